@@ -1,0 +1,244 @@
+"""CPU oracle -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+ctypes/numpy front end of ``oracle/pose_oracle.c``, the plain-C restatement of the
+reference's pose-geometry hot path (models/add_loss.py:156-215, models/pose_loss.py:19-61,
+models/pose_net_rgb_geometric.py:93-109, models/pose_net_rgbd_geometric.py:56-85 of
+SFR-Vision/6d-pose-estimation).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
+legs of ``bench.py`` may import this package, and only as the checker or the timed CPU
+baseline.  Nothing under ``6d-pose-estimation_b200/`` imports it.
+
+Parity status: pinned against the reference itself through ``tests/golden/`` (see
+``oracle/gen_golden.py`` and ``tests/test_oracle_golden.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpose_oracle.so")
+_lib = None
+
+SYMMETRIC_OBJECT_IDS = frozenset({9, 10})  # models/add_loss.py:10
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with the committed Makefile (gcc, no reference sources)."""
+    src = os.path.join(_HERE, "pose_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "CC=gcc"], check=True, capture_output=True)
+    return _SO
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        fp, ip, dp, bp, lp = (C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double),
+                              C.POINTER(C.c_uint8), C.POINTER(C.c_int64))
+        L.p6o_aten_sum_f32.restype = C.c_float
+        L.p6o_aten_sum_f32.argtypes = [fp, C.c_int64]
+        L.p6o_aten_mean_f32.restype = C.c_float
+        L.p6o_aten_mean_f32.argtypes = [fp, C.c_int64]
+        L.p6o_quat_to_mat.restype = None
+        L.p6o_quat_to_mat.argtypes = [fp, fp]
+        L.p6o_transform.restype = None
+        L.p6o_transform.argtypes = [fp, C.c_int64, fp, fp, fp]
+        L.p6o_add_eval.restype = C.c_int
+        L.p6o_add_eval.argtypes = [fp, ip, ip, dp, bp, C.c_int, fp, fp, fp, fp, lp, C.c_int64,
+                                   C.c_int, fp, fp, bp, bp, C.c_int]
+        L.p6o_pose_loss.restype = C.c_int
+        L.p6o_pose_loss.argtypes = [fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_int,
+                                    fp, fp, fp, fp, fp, fp]
+        L.p6o_pinhole.restype = None
+        L.p6o_pinhole.argtypes = [fp, fp, fp, C.c_int, C.c_int64, fp, fp, fp]
+        L.p6o_depth_backproject.restype = None
+        L.p6o_depth_backproject.argtypes = [fp, C.c_int, C.c_int, fp, fp, C.c_int, C.c_int64,
+                                            C.c_float, fp]
+        L.p6o_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty)) if a is not None else None
+
+
+def max_threads() -> int:
+    return int(lib().p6o_max_threads())
+
+
+def aten_sum(x) -> np.float32:
+    x = _f32(x).ravel()
+    return np.float32(lib().p6o_aten_sum_f32(_ptr(x, C.c_float), x.size))
+
+
+def aten_mean(x) -> np.float32:
+    x = _f32(x).ravel()
+    return np.float32(lib().p6o_aten_mean_f32(_ptr(x, C.c_float), x.size))
+
+
+def quat_to_mat(q) -> np.ndarray:
+    """[B,4] scalar-last quaternions -> [B,3,3] (models/add_loss.py:203-215)."""
+    q = _f32(q).reshape(-1, 4)
+    out = np.empty((q.shape[0], 3, 3), np.float32)
+    for b in range(q.shape[0]):
+        lib().p6o_quat_to_mat(_ptr(q[b], C.c_float), _ptr(out[b], C.c_float))
+    return out
+
+
+def transform(mesh, q, t) -> np.ndarray:
+    mesh = _f32(mesh).reshape(-1, 3)
+    q, t = _f32(q).ravel(), _f32(t).ravel()
+    out = np.empty_like(mesh)
+    lib().p6o_transform(_ptr(mesh, C.c_float), mesh.shape[0], _ptr(q, C.c_float),
+                        _ptr(t, C.c_float), _ptr(out, C.c_float))
+    return out
+
+
+class MeshTable:
+    """Host mirror of ``ADDLoss.points`` / ``ADDLoss.diameters`` (models/add_loss.py:21-22)
+    flattened for the C entry points: slot = object id."""
+
+    def __init__(self, points: dict, diameters: dict | None = None, symmetric_ids=SYMMETRIC_OBJECT_IDS):
+        diameters = diameters or {}
+        ids = [int(k) for k in points.keys()]
+        if any(i < 0 for i in ids):
+            raise ValueError("negative object id")
+        self.n_slots = (max(ids) + 1) if ids else 1
+        self.offsets = np.zeros(self.n_slots, np.int32)
+        self.counts = np.zeros(self.n_slots, np.int32)
+        self.diameters = np.full(self.n_slots, 0.1, np.float64)  # .get(oid, 0.1), add_loss.py:175
+        self.symmetric = np.zeros(self.n_slots, np.uint8)
+        chunks, off = [], 0
+        for oid in sorted(ids):
+            m = _f32(points[oid]).reshape(-1, 3)
+            self.offsets[oid], self.counts[oid] = off, m.shape[0]
+            off += m.shape[0]
+            chunks.append(m)
+            if oid in diameters:
+                self.diameters[oid] = float(diameters[oid])
+            self.symmetric[oid] = 1 if oid in symmetric_ids else 0
+        self.xyz = np.concatenate(chunks, 0) if chunks else np.zeros((1, 3), np.float32)
+
+
+def add_eval(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids, want_adds=True, n_threads=1):
+    """Per-pose ADD, ADD-S, ADD-0.1d hit and validity (models/add_loss.py:168-195)."""
+    pq, pt, gq, gt = (_f32(pred_q).reshape(-1, 4), _f32(pred_t).reshape(-1, 3),
+                      _f32(gt_q).reshape(-1, 4), _f32(gt_t).reshape(-1, 3))
+    obj = np.ascontiguousarray(obj_ids, dtype=np.int64).ravel()
+    B = obj.shape[0]
+    add = np.zeros(B, np.float32)
+    adds = np.zeros(B, np.float32)
+    hit = np.zeros(B, np.uint8)
+    valid = np.zeros(B, np.uint8)
+    rc = lib().p6o_add_eval(
+        _ptr(table.xyz, C.c_float), _ptr(table.offsets, C.c_int32), _ptr(table.counts, C.c_int32),
+        _ptr(table.diameters, C.c_double), _ptr(table.symmetric, C.c_uint8), table.n_slots,
+        _ptr(pq, C.c_float), _ptr(pt, C.c_float), _ptr(gq, C.c_float), _ptr(gt, C.c_float),
+        _ptr(obj, C.c_int64), B, 1 if want_adds else 0, _ptr(add, C.c_float), _ptr(adds, C.c_float),
+        _ptr(hit, C.c_uint8), _ptr(valid, C.c_uint8), int(n_threads))
+    if rc != 0:
+        raise MemoryError("oracle add_eval failed")
+    return add, adds, hit, valid
+
+
+def eval_metrics(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids, n_threads=1) -> dict:
+    """The dict ``ADDLoss.eval_metrics`` returns (models/add_loss.py:197-201): float64
+    host means over the valid poses, int 0 when none is valid."""
+    add, adds, hit, valid = add_eval(table, pred_q, pred_t, gt_q, gt_t, obj_ids, True, n_threads)
+    v = valid.astype(bool)
+    if not v.any():
+        return {"add_mean": 0, "add_s_mean": 0, "add_01d_acc": 0}
+    return {
+        "add_mean": np.mean([float(x) for x in add[v]]) * 1000,
+        "add_s_mean": np.mean([float(x) for x in adds[v]]) * 1000,
+        "add_01d_acc": np.mean([float(x) for x in hit[v]]) * 100,
+    }
+
+
+def add_forward(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids) -> np.float32:
+    """Value of ``ADDLoss.forward`` (models/add_loss.py:101-150): per object group, the
+    float32 ATen sum of the per-sample ADD (or ADD-S for symmetric ids), accumulated in
+    first-appearance order, divided by the number of valid samples."""
+    add, adds, _, valid = add_eval(table, pred_q, pred_t, gt_q, gt_t, obj_ids, True)
+    obj = np.asarray(obj_ids, np.int64).ravel()
+    order, groups = [], {}
+    for i, o in enumerate(obj):
+        if valid[i]:
+            if int(o) not in groups:
+                groups[int(o)] = []
+                order.append(int(o))
+            groups[int(o)].append(i)
+    total, count = np.float32(0.0), 0
+    for o in order:
+        idx = groups[o]
+        vals = (adds if table.symmetric[o] else add)[idx]
+        total = np.float32(total + aten_sum(vals))
+        count += len(idx)
+    if count == 0:
+        return np.float32(0.0)
+    return np.float32(total / np.float32(count))
+
+
+def pose_loss(pred_q, pred_t, gt_q, gt_t, rot_weight=1.0, trans_weight=1.0, mode="geodesic",
+              want_grads=True):
+    """PoseLoss.forward (+ analytic grads) -- models/pose_loss.py:19-61."""
+    pq, pt, gq, gt = (_f32(pred_q).reshape(-1, 4), _f32(pred_t).reshape(-1, 3),
+                      _f32(gt_q).reshape(-1, 4), _f32(gt_t).reshape(-1, 3))
+    B = pq.shape[0]
+    loss, rot, tr = (np.zeros(1, np.float32) for _ in range(3))
+    rows = np.zeros(B, np.float32)
+    gq_ = np.zeros((B, 4), np.float32) if want_grads else None
+    gt_ = np.zeros((B, 3), np.float32) if want_grads else None
+    rc = lib().p6o_pose_loss(_ptr(pq, C.c_float), _ptr(pt, C.c_float), _ptr(gq, C.c_float),
+                             _ptr(gt, C.c_float), B, float(rot_weight), float(trans_weight),
+                             0 if mode == "geodesic" else 1, _ptr(loss, C.c_float),
+                             _ptr(rot, C.c_float), _ptr(tr, C.c_float), _ptr(rows, C.c_float),
+                             _ptr(gq_, C.c_float), _ptr(gt_, C.c_float))
+    if rc != 0:
+        raise ValueError("oracle pose_loss failed (B must be > 0)")
+    return {"loss": loss[0], "rot": rot[0], "trans": tr[0], "rows": rows, "grad_q": gq_, "grad_t": gt_}
+
+
+def _k_args(K, B):
+    K = _f32(K)
+    if K.ndim == 2:
+        return K.reshape(9), 0
+    return K.reshape(B, 9), 1
+
+
+def pinhole(z_pred, bbox_center, K, grad_out=None):
+    """models/pose_net_rgb_geometric.py:93-109; returns (out[B,3], grad_z[B,1] or None)."""
+    z = _f32(z_pred).reshape(-1)
+    B = z.shape[0]
+    uv = _f32(bbox_center).reshape(B, 2)
+    Kf, kb = _k_args(K, B)
+    out = np.zeros((B, 3), np.float32)
+    go = _f32(grad_out).reshape(B, 3) if grad_out is not None else None
+    gz = np.zeros(B, np.float32) if grad_out is not None else None
+    lib().p6o_pinhole(_ptr(z, C.c_float), _ptr(uv, C.c_float), _ptr(Kf, C.c_float), kb, B,
+                      _ptr(out, C.c_float), _ptr(go, C.c_float), _ptr(gz, C.c_float))
+    return out, (gz.reshape(B, 1) if gz is not None else None)
+
+
+def depth_backproject(depth_raw, bbox_center, K, clamp_hi=223.0):
+    """models/pose_net_rgbd_geometric.py:56-85."""
+    d = _f32(depth_raw)
+    B, H, W = d.shape
+    uv = _f32(bbox_center).reshape(B, 2)
+    Kf, kb = _k_args(K, B)
+    out = np.zeros((B, 3), np.float32)
+    lib().p6o_depth_backproject(_ptr(d, C.c_float), H, W, _ptr(uv, C.c_float), _ptr(Kf, C.c_float),
+                                kb, B, float(clamp_hi), _ptr(out, C.c_float))
+    return out
