@@ -1,0 +1,593 @@
+// p6d_add.cu -- ADD / ADD-S / ADD-0.1d evaluation kernels for sm_100a.
+//
+// Replaces the per-pose Python loop of ADDLoss.eval_metrics
+// (reference models/add_loss.py:156-201: ~12 eager launches and 4 host syncs per pose,
+// a [N,N,3] temporary per pose) with one launch per batch:
+//
+//   add_warp_kernel   (a) one warp per pose: quat->R (x2), model-point transform (x2),
+//                         |pred_i - gt_i|, ordered mean, threshold.  No shared memory:
+//                         the mesh (<= 24 KB) is read through L1 with coalesced loads.
+//   adds_cta_kernel   (b) one CTA per pose, persistent grid: the object's mesh is staged
+//                         into shared memory by one TMA bulk copy (re-staged only when
+//                         the object changes), the gt cloud is written to shared memory
+//                         as SoA quads, each thread keeps K pred points in registers and
+//                         scans the gt cloud with packed FP32 (FADD2/FMUL2/FFMA2) distance
+//                         tiles and 3-input NaN-propagating minima (FMNMX3); nothing of
+//                         size N^2 is ever materialised.  ADD comes out of the same pass.
+//
+// Arithmetic is the reference's, rounding for rounding (DESIGN.md "Arithmetic"); the
+// final means use aten_sum_warp so the float32 results equal the CPU reference's bits.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "p6d_common.cuh"
+
+namespace p6d {
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) in %s", static_cast<int>(e), cudaGetErrorString(e), what);
+    // clear the sticky-free error state so that later calls report their own failure
+    cudaGetLastError();
+    return P6D_ECUDA;
+}
+
+// ------------------------------------------------------------------ kernel (a): ADD
+constexpr int ADD_WARPS = 8;
+
+struct EvalArgs {
+    const float* soa;
+    const SlotInfo* slots;
+    int n_slots;
+    const float* pq;
+    const float* pt;
+    const float* gq;
+    const float* gt;
+    const int64_t* obj;
+    const int32_t* order;
+    int64_t B;
+    float* add;
+    float* adds;
+    uint8_t* hit;
+    uint8_t* valid;
+    p6d_accumulators acc;
+    int has_acc;
+};
+
+__device__ __forceinline__ void accumulate(const EvalArgs& a, int64_t oid, bool is_hit, float add,
+                                           float adds, bool has_adds) {
+    if (!a.has_acc) return;
+    if (a.acc.valid) atomicAdd(reinterpret_cast<unsigned long long*>(a.acc.valid + oid), 1ull);
+    if (a.acc.hits && is_hit) atomicAdd(reinterpret_cast<unsigned long long*>(a.acc.hits + oid), 1ull);
+    if (a.acc.add_sum) atomicAdd(a.acc.add_sum + oid, static_cast<double>(add));
+    if (a.acc.adds_sum && has_adds) atomicAdd(a.acc.adds_sum + oid, static_cast<double>(adds));
+}
+
+__global__ void __launch_bounds__(ADD_WARPS * 32) add_warp_kernel(EvalArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = static_cast<int64_t>(blockIdx.x) * ADD_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * ADD_WARPS;
+    for (int64_t it = warp; it < a.B; it += nwarps) {
+        const int64_t b = a.order ? a.order[it] : it;
+        const int64_t oid = a.obj[b];
+        const bool known = oid >= 0 && oid < a.n_slots && a.slots[oid].count > 0;
+        if (!known) {
+            if (lane == 0) {
+                a.add[b] = 0.0f;
+                a.hit[b] = 0;
+                a.valid[b] = 0;
+            }
+            continue;
+        }
+        const SlotInfo s = a.slots[oid];
+        const float* mx = a.soa + s.soa_offset;
+        const float* my = mx + s.padded;
+        const float* mz = my + s.padded;
+        float Rp[9], Rg[9], tp[3], tg[3], q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(a.pq + 4 * b + k);
+        quat_to_mat(q, Rp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(a.gq + 4 * b + k);
+        quat_to_mat(q, Rg);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            tp[k] = __ldg(a.pt + 3 * b + k);
+            tg[k] = __ldg(a.gt + 3 * b + k);
+        }
+        const int mode = s.xform_mode;
+        auto dist = [&](int e) -> float {
+            const float x = __ldg(mx + e), y = __ldg(my + e), z = __ldg(mz + e);
+            float px, py, pz, gx, gy, gz;
+            xform_point(mode, x, y, z, Rp, tp, px, py, pz);
+            xform_point(mode, x, y, z, Rg, tg, gx, gy, gz);
+            return __fsqrt_rn(sq3(__fsub_rn(px, gx), __fsub_rn(py, gy), __fsub_rn(pz, gz)));
+        };
+        const float mean = aten_mean_warp(dist, s.count, lane);
+        if (lane == 0) {
+            const bool is_hit = static_cast<double>(mean) < s.threshold;
+            a.add[b] = mean;
+            a.hit[b] = is_hit ? 1 : 0;
+            a.valid[b] = 1;
+            accumulate(a, oid, is_hit, mean, 0.0f, false);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ kernel (b): ADD-S
+constexpr int ADDS_T = 256;  // threads per CTA
+constexpr int ADDS_K = 8;    // pred points per thread
+constexpr float SENTINEL = 1.0e18f;  // padded gt coordinate: (p - 1e18)^2 * 3 < FLT_MAX, never the min
+
+// dynamic shared memory layout (floats), for a table whose largest mesh has Nmax points:
+//   mesh  [3 * Npmax]            staged by TMA; x | y | z, each Np long
+//   gt    [3 * Ngmax]            gt cloud as SoA, padded with SENTINEL to 4*S
+//   dadd  [Nmax], dadds [Nmax]   per-point distances for the ordered means
+//   mbar  8 bytes
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t adds_smem_bytes(int nmax) {
+    const int np = round_up(nmax, 4);
+    const int ng = round_up(nmax, 4) + 4 * 32;
+    return sizeof(float) * (3 * (size_t)np + 3 * (size_t)ng + 2 * (size_t)round_up(nmax, 4)) + 16;
+}
+
+__device__ __forceinline__ void pair_tile(float px, float py, float pz, float2 gx, float2 gy, float2 gz,
+                                          float& m) {
+    // two (pred, gt) pairs: 3 FADD2 + FMUL2 + 2 FFMA2 + FMNMX3.NAN
+    const float2 dx = sub2(make_float2(px, px), gx);
+    const float2 dy = sub2(make_float2(py, py), gy);
+    const float2 dz = sub2(make_float2(pz, pz), gz);
+    float2 s = mul2(dx, dx);
+    s = fma2(dy, dy, s);
+    s = fma2(dz, dz, s);
+    m = min3_nan(m, s.x, s.y);
+}
+
+__global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nmax) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int npmax = round_up(nmax, 4);
+    const int ngmax = npmax + 4 * 32;
+    float* s_mesh = reinterpret_cast<float*>(smem_raw);
+    float* s_gt = s_mesh + 3 * npmax;
+    float* s_dadd = s_gt + 3 * ngmax;
+    float* s_dadds = s_dadd + npmax;
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dadds + npmax);
+    __shared__ float s_pose[14];
+    __shared__ long long s_oid;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    long long staged_oid = -1;
+    uint32_t phase = 0;
+
+    for (int64_t it = blockIdx.x; it < a.B; it += gridDim.x) {
+        const int64_t b = a.order ? a.order[it] : it;
+        if (tid < 4) s_pose[tid] = __ldg(a.pq + 4 * b + tid);
+        else if (tid < 8) s_pose[tid] = __ldg(a.gq + 4 * b + tid - 4);
+        else if (tid < 11) s_pose[tid] = __ldg(a.pt + 3 * b + tid - 8);
+        else if (tid < 14) s_pose[tid] = __ldg(a.gt + 3 * b + tid - 11);
+        else if (tid == 32) s_oid = a.obj[b];
+        __syncthreads();  // also: previous iteration's readers of s_gt / s_dadd* are done
+        const long long oid = s_oid;
+        const bool known = oid >= 0 && oid < a.n_slots && a.slots[oid].count > 0;
+        if (!known) {  // CTA-uniform
+            if (tid == 0) {
+                a.add[b] = 0.0f;
+                a.adds[b] = 0.0f;
+                a.hit[b] = 0;
+                a.valid[b] = 0;
+            }
+            __syncthreads();
+            continue;
+        }
+        const SlotInfo s = a.slots[oid];
+        const int n = s.count, np = s.padded;
+        if (oid != staged_oid) {
+            // stage the mesh: one elected thread arms the barrier and issues the bulk copy
+            if (tid == 0) {
+                fence_proxy_async();
+                const uint32_t bytes = 3u * static_cast<uint32_t>(np) * sizeof(float);
+                mbar_arrive_expect_tx(s_bar, bytes);
+                tma_bulk_g2s(s_mesh, a.soa + s.soa_offset, bytes, s_bar);
+            }
+            mbar_wait(s_bar, phase);
+            phase ^= 1;
+            staged_oid = oid;
+        }
+        const float* mx = s_mesh;
+        const float* my = s_mesh + np;
+        const float* mz = s_mesh + 2 * np;
+
+        float Rp[9], Rg[9], tp[3], tg[3];
+        quat_to_mat(s_pose, Rp);
+        quat_to_mat(s_pose + 4, Rg);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            tp[k] = s_pose[8 + k];
+            tg[k] = s_pose[11 + k];
+        }
+        const int mode = s.xform_mode;
+
+        // gt split: S lanes share one group of K pred points and scan 1/S of the gt quads
+        int S = 1;
+        while (S < 32 && (ADDS_T / (2 * S)) * ADDS_K >= n) S *= 2;
+        const int groups = ADDS_T / S;
+        const int ng = round_up(n, 4 * S);
+        float* gx = s_gt;
+        float* gy = s_gt + ng;
+        float* gz = s_gt + 2 * ng;
+
+        // phase B: gt cloud -> shared memory, ADD distances
+        for (int i = tid; i < ng; i += ADDS_T) {
+            if (i < n) {
+                const float x = mx[i], y = my[i], z = mz[i];
+                float px, py, pz, qx, qy, qz;
+                xform_point(mode, x, y, z, Rp, tp, px, py, pz);
+                xform_point(mode, x, y, z, Rg, tg, qx, qy, qz);
+                gx[i] = qx;
+                gy[i] = qy;
+                gz[i] = qz;
+                s_dadd[i] = __fsqrt_rn(sq3(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
+            } else {
+                gx[i] = SENTINEL;
+                gy[i] = SENTINEL;
+                gz[i] = SENTINEL;
+            }
+        }
+        __syncthreads();
+
+        // phase C: all-pairs scan
+        const int g = tid / S, sp = tid % S;
+        const float4* gx4 = reinterpret_cast<const float4*>(gx);
+        const float4* gy4 = reinterpret_cast<const float4*>(gy);
+        const float4* gz4 = reinterpret_cast<const float4*>(gz);
+        const int nquads = ng >> 2;
+        for (int base = 0; base < n; base += groups * ADDS_K) {
+            float px[ADDS_K], py[ADDS_K], pz[ADDS_K], m[ADDS_K];
+#pragma unroll
+            for (int k = 0; k < ADDS_K; ++k) {
+                const int i = base + g + k * groups;
+                const int ii = i < n ? i : 0;
+                xform_point(mode, mx[ii], my[ii], mz[ii], Rp, tp, px[k], py[k], pz[k]);
+                m[k] = __int_as_float(0x7f800000);  // +inf
+            }
+#pragma unroll 1
+            for (int qd = sp; qd < nquads; qd += S) {
+                const float4 X = gx4[qd], Y = gy4[qd], Z = gz4[qd];
+#pragma unroll
+                for (int k = 0; k < ADDS_K; ++k) {
+                    pair_tile(px[k], py[k], pz[k], make_float2(X.x, X.y), make_float2(Y.x, Y.y),
+                              make_float2(Z.x, Z.y), m[k]);
+                    pair_tile(px[k], py[k], pz[k], make_float2(X.z, X.w), make_float2(Y.z, Y.w),
+                              make_float2(Z.z, Z.w), m[k]);
+                }
+            }
+            for (int o = 1; o < S; o <<= 1) {
+#pragma unroll
+                for (int k = 0; k < ADDS_K; ++k) m[k] = min_nan(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+            }
+            if (sp == 0) {
+#pragma unroll
+                for (int k = 0; k < ADDS_K; ++k) {
+                    const int i = base + g + k * groups;
+                    // sqrt is monotone and correctly rounded: sqrt(min s) == min sqrt(s)
+                    if (i < n) s_dadds[i] = __fsqrt_rn(m[k]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // phase D: ordered means (ATen summation order), decision, outputs
+        if (tid < 32) {
+            const float add = aten_mean_warp([&](int e) { return s_dadd[e]; }, n, lane);
+            const float adds = aten_mean_warp([&](int e) { return s_dadds[e]; }, n, lane);
+            if (lane == 0) {
+                const float eff = s.symmetric ? adds : add;
+                const bool is_hit = static_cast<double>(eff) < s.threshold;
+                a.add[b] = add;
+                a.adds[b] = adds;
+                a.hit[b] = is_hit ? 1 : 0;
+                a.valid[b] = 1;
+                accumulate(a, oid, is_hit, add, adds, true);
+            }
+        }
+        // the __syncthreads at the top of the next iteration protects s_gt / s_dadd*
+    }
+}
+
+// ------------------------------------------------------------------ quat -> R (API parity)
+__global__ void quat_to_mat_kernel(const float* __restrict__ q, int64_t B, float* __restrict__ R) {
+    const int64_t b = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float qq[4], r[9];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) qq[k] = q[4 * b + k];
+    quat_to_mat(qq, r);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[9 * b + k] = r[k];
+}
+
+static int max_optin_smem(int device, int* out) {
+    int v = 0;
+    P6D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *out = v;
+    return P6D_OK;
+}
+
+static int adds_max_points_for(int smem_limit) {
+    // largest n with adds_smem_bytes(n) + static smem <= limit
+    int lo = 1, hi = 1 << 16;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        if (adds_smem_bytes(mid) + 256 <= static_cast<size_t>(smem_limit)) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_adds, cudaStream_t st,
+                       int* launches) {
+    if (args.B == 0) return P6D_OK;
+    if (!want_adds) {
+        int64_t blocks = (args.B + ADD_WARPS - 1) / ADD_WARPS;
+        const int64_t cap = static_cast<int64_t>(t->sm_count) * 8;
+        if (blocks > cap) blocks = cap;
+        add_warp_kernel<<<static_cast<unsigned>(blocks), ADD_WARPS * 32, 0, st>>>(args);
+        P6D_CUDA(cudaGetLastError());
+        if (launches) ++*launches;
+        return P6D_OK;
+    }
+    int limit = 0;
+    int rc = max_optin_smem(t->device, &limit);
+    if (rc) return rc;
+    const size_t smem = adds_smem_bytes(t->max_count);
+    if (smem + 256 > static_cast<size_t>(limit)) {
+        set_error("largest mesh has %d points; the ADD-S kernel holds the mesh, the gt cloud and two "
+                  "distance rows in shared memory and accepts at most %d points on this device",
+                  t->max_count, adds_max_points_for(limit));
+        return P6D_ETOOBIG;
+    }
+    P6D_CUDA(cudaFuncSetAttribute(adds_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    int per_sm = 0;
+    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_cta_kernel, ADDS_T, smem));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = static_cast<int64_t>(t->sm_count) * per_sm;
+    if (grid > args.B) grid = args.B;
+    adds_cta_kernel<<<static_cast<unsigned>(grid), ADDS_T, smem, st>>>(args, t->max_count);
+    P6D_CUDA(cudaGetLastError());
+    if (launches) ++*launches;
+    return P6D_OK;
+}
+
+}  // namespace p6d
+
+using namespace p6d;
+
+// ====================================================================== C ABI
+extern "C" {
+
+int p6d_version(void) { return P6D_VERSION; }
+
+const char* p6d_last_error(void) { return g_err; }
+
+int p6d_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz,
+                    int64_t* smem_per_block_optin) {
+    int v = 0;
+    if (sm_count) { P6D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device)); *sm_count = v; }
+    if (cc_major) { P6D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, device)); *cc_major = v; }
+    if (cc_minor) { P6D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, device)); *cc_minor = v; }
+    if (sm_clock_khz) { P6D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrClockRate, device)); *sm_clock_khz = v; }
+    if (smem_per_block_optin) {
+        P6D_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        *smem_per_block_optin = v;
+    }
+    return P6D_OK;
+}
+
+int p6d_adds_max_points(int device, int* max_points) {
+    if (!max_points) { set_error("max_points is NULL"); return P6D_EINVAL; }
+    int limit = 0;
+    int rc = max_optin_smem(device, &limit);
+    if (rc) return rc;
+    *max_points = adds_max_points_for(limit);
+    return P6D_OK;
+}
+
+int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_t* counts,
+                          const double* diameters, const uint8_t* symmetric, int n_slots, int device,
+                          p6d_mesh_table** out) {
+    if (!out || n_slots < 1 || !offsets || !counts || !diameters || !symmetric) {
+        set_error("p6d_mesh_table_create: bad arguments (n_slots=%d)", n_slots);
+        return P6D_EINVAL;
+    }
+    *out = nullptr;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    p6d_mesh_table* t = new (std::nothrow) p6d_mesh_table();
+    if (!t) { set_error("out of host memory"); return P6D_ENOMEM; }
+    t->device = device;
+    t->n_slots = n_slots;
+    t->h_slots = static_cast<SlotInfo*>(calloc(n_slots, sizeof(SlotInfo)));
+    if (!t->h_slots) { delete t; set_error("out of host memory"); return P6D_ENOMEM; }
+    size_t total = 0;
+    for (int s = 0; s < n_slots; ++s) {
+        if (counts[s] < 0) { free(t->h_slots); delete t; set_error("negative count in slot %d", s); return P6D_EINVAL; }
+        SlotInfo& si = t->h_slots[s];
+        si.count = counts[s];
+        si.padded = round_up(counts[s], 4);
+        si.soa_offset = static_cast<int64_t>(total);
+        si.threshold = 0.1 * diameters[s];
+        si.symmetric = symmetric[s] ? 1 : 0;
+        si.xform_mode = counts[s] >= 11 ? XF_FMA_CHAIN : (counts[s] == 1 ? XF_N1 : XF_SMALL);
+        total += 3 * static_cast<size_t>(si.padded);
+        if (counts[s] > t->max_count) t->max_count = counts[s];
+        if (counts[s] > 0 && !xyz) { free(t->h_slots); delete t; set_error("xyz is NULL"); return P6D_EINVAL; }
+    }
+    std::vector<float> soa(total > 0 ? total : 4, 0.0f);
+    for (int s = 0; s < n_slots; ++s) {
+        const SlotInfo& si = t->h_slots[s];
+        const float* src = xyz + 3 * static_cast<size_t>(offsets[s]);
+        float* x = soa.data() + si.soa_offset;
+        for (int i = 0; i < si.count; ++i) {
+            x[i] = src[3 * i];
+            x[si.padded + i] = src[3 * i + 1];
+            x[2 * si.padded + i] = src[3 * i + 2];
+        }
+    }
+    int rc = P6D_OK;
+    auto fail = [&](cudaError_t e, const char* what) {
+        rc = cuda_fail(e, what);
+        if (t->d_soa) cudaFree(t->d_soa);
+        if (t->d_slots) cudaFree(t->d_slots);
+        free(t->h_slots);
+        delete t;
+        return rc;
+    };
+    cudaError_t e;
+    if ((e = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess)
+        return fail(e, "cudaDeviceGetAttribute");
+    if ((e = cudaMalloc(&t->d_soa, soa.size() * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(soa)");
+    if ((e = cudaMalloc(&t->d_slots, n_slots * sizeof(SlotInfo))) != cudaSuccess) return fail(e, "cudaMalloc(slots)");
+    if ((e = cudaMemcpy(t->d_soa, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(soa)");
+    if ((e = cudaMemcpy(t->d_slots, t->h_slots, n_slots * sizeof(SlotInfo), cudaMemcpyHostToDevice)) != cudaSuccess)
+        return fail(e, "cudaMemcpy(slots)");
+    *out = t;
+    return P6D_OK;
+}
+
+int p6d_mesh_table_destroy(p6d_mesh_table* t) {
+    if (!t) return P6D_OK;
+    DeviceGuard guard(t->device);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    if (t->d_stage) cudaFree(t->d_stage);
+    if (t->h_pinned) cudaFreeHost(t->h_pinned);
+    if (t->d_soa) cudaFree(t->d_soa);
+    if (t->d_slots) cudaFree(t->d_slots);
+    free(t->h_slots);
+    delete t;
+    return P6D_OK;
+}
+
+int p6d_add_eval(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                 const float* gt, const int64_t* obj, const int32_t* order, int64_t B, float* add,
+                 float* adds, uint8_t* hit, uint8_t* valid, const p6d_accumulators* acc, void* stream) {
+    if (!table || B < 0 || (B > 0 && (!pq || !pt || !gq || !gt || !obj || !add || !hit || !valid))) {
+        set_error("p6d_add_eval: bad arguments");
+        return P6D_EINVAL;
+    }
+    DeviceGuard guard(table->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    EvalArgs a{};
+    a.soa = table->d_soa; a.slots = table->d_slots; a.n_slots = table->n_slots;
+    a.pq = pq; a.pt = pt; a.gq = gq; a.gt = gt; a.obj = obj; a.order = order; a.B = B;
+    a.add = add; a.adds = adds; a.hit = hit; a.valid = valid;
+    if (acc) { a.acc = *acc; a.has_acc = 1; }
+    return launch_eval(table, a, adds != nullptr, static_cast<cudaStream_t>(stream), nullptr);
+}
+
+static int ensure_staging(p6d_mesh_table* t, size_t dev_bytes, size_t pin_bytes) {
+    if (!t->stream) P6D_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+    if (t->stage_bytes < dev_bytes) {
+        if (t->d_stage) cudaFree(t->d_stage);
+        t->d_stage = nullptr; t->stage_bytes = 0;
+        P6D_CUDA(cudaMalloc(&t->d_stage, dev_bytes));
+        t->stage_bytes = dev_bytes;
+    }
+    if (t->pinned_bytes < pin_bytes) {
+        if (t->h_pinned) cudaFreeHost(t->h_pinned);
+        t->h_pinned = nullptr; t->pinned_bytes = 0;
+        P6D_CUDA(cudaMallocHost(&t->h_pinned, pin_bytes));
+        t->pinned_bytes = pin_bytes;
+    }
+    return P6D_OK;
+}
+
+int p6d_add_eval_host(p6d_mesh_table* t, const float* pq, const float* pt, const float* gq,
+                      const float* gt, const int64_t* obj, int64_t B, int want_adds, float* add,
+                      float* adds, uint8_t* hit, uint8_t* valid, int64_t* acc_hits, int64_t* acc_valid,
+                      double* acc_add_sum, double* acc_adds_sum, int* gpu_launches) {
+    if (!t || B < 0 || (B > 0 && (!pq || !pt || !gq || !gt || !obj))) {
+        set_error("p6d_add_eval_host: bad arguments");
+        return P6D_EINVAL;
+    }
+    if (gpu_launches) *gpu_launches = 0;
+    DeviceGuard guard(t->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    const size_t nB = static_cast<size_t>(B), ns = static_cast<size_t>(t->n_slots);
+    // device layout: [acc: hits|valid|add_sum|adds_sum (8 B each x ns)] [obj 8B] [pq 16] [gq 16] [pt 12] [gt 12]
+    //                [add 4] [adds 4] [hit 1] [valid 1]
+    const size_t acc_bytes = 4 * 8 * ns;
+    size_t off = acc_bytes;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_obj = take(8 * nB), o_pq = take(16 * nB), o_gq = take(16 * nB), o_pt = take(12 * nB),
+                 o_gt = take(12 * nB), o_add = take(4 * nB), o_adds = take(4 * nB), o_hit = take(nB),
+                 o_valid = take(nB);
+    int rc = ensure_staging(t, off, acc_bytes);
+    if (rc) return rc;
+    char* d = static_cast<char*>(t->d_stage);
+    cudaStream_t st = t->stream;
+    P6D_CUDA(cudaMemsetAsync(d, 0, acc_bytes, st));
+    P6D_CUDA(cudaMemcpyAsync(d + o_obj, obj, 8 * nB, cudaMemcpyHostToDevice, st));
+    P6D_CUDA(cudaMemcpyAsync(d + o_pq, pq, 16 * nB, cudaMemcpyHostToDevice, st));
+    P6D_CUDA(cudaMemcpyAsync(d + o_gq, gq, 16 * nB, cudaMemcpyHostToDevice, st));
+    P6D_CUDA(cudaMemcpyAsync(d + o_pt, pt, 12 * nB, cudaMemcpyHostToDevice, st));
+    P6D_CUDA(cudaMemcpyAsync(d + o_gt, gt, 12 * nB, cudaMemcpyHostToDevice, st));
+    EvalArgs a{};
+    a.soa = t->d_soa; a.slots = t->d_slots; a.n_slots = t->n_slots;
+    a.pq = reinterpret_cast<float*>(d + o_pq); a.gq = reinterpret_cast<float*>(d + o_gq);
+    a.pt = reinterpret_cast<float*>(d + o_pt); a.gt = reinterpret_cast<float*>(d + o_gt);
+    a.obj = reinterpret_cast<int64_t*>(d + o_obj); a.order = nullptr; a.B = B;
+    a.add = reinterpret_cast<float*>(d + o_add); a.adds = want_adds ? reinterpret_cast<float*>(d + o_adds) : nullptr;
+    a.hit = reinterpret_cast<uint8_t*>(d + o_hit); a.valid = reinterpret_cast<uint8_t*>(d + o_valid);
+    a.acc.hits = reinterpret_cast<int64_t*>(d); a.acc.valid = reinterpret_cast<int64_t*>(d + 8 * ns);
+    a.acc.add_sum = reinterpret_cast<double*>(d + 16 * ns); a.acc.adds_sum = reinterpret_cast<double*>(d + 24 * ns);
+    a.has_acc = 1;
+    rc = launch_eval(t, a, want_adds != 0, st, gpu_launches);
+    if (rc) return rc;
+    if (add) P6D_CUDA(cudaMemcpyAsync(add, d + o_add, 4 * nB, cudaMemcpyDeviceToHost, st));
+    if (adds && want_adds) P6D_CUDA(cudaMemcpyAsync(adds, d + o_adds, 4 * nB, cudaMemcpyDeviceToHost, st));
+    if (hit) P6D_CUDA(cudaMemcpyAsync(hit, d + o_hit, nB, cudaMemcpyDeviceToHost, st));
+    if (valid) P6D_CUDA(cudaMemcpyAsync(valid, d + o_valid, nB, cudaMemcpyDeviceToHost, st));
+    P6D_CUDA(cudaMemcpyAsync(t->h_pinned, d, acc_bytes, cudaMemcpyDeviceToHost, st));
+    P6D_CUDA(cudaStreamSynchronize(st));
+    const char* h = static_cast<const char*>(t->h_pinned);
+    if (acc_hits) memcpy(acc_hits, h, 8 * ns);
+    if (acc_valid) memcpy(acc_valid, h + 8 * ns, 8 * ns);
+    if (acc_add_sum) memcpy(acc_add_sum, h + 16 * ns, 8 * ns);
+    if (acc_adds_sum) memcpy(acc_adds_sum, h + 24 * ns, 8 * ns);
+    return P6D_OK;
+}
+
+int p6d_quat_to_mat(const float* q, int64_t B, float* R, int device, void* stream) {
+    if (B < 0 || (B > 0 && (!q || !R))) { set_error("p6d_quat_to_mat: bad arguments"); return P6D_EINVAL; }
+    if (B == 0) return P6D_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    const int threads = 256;
+    quat_to_mat_kernel<<<static_cast<unsigned>((B + threads - 1) / threads), threads, 0,
+                         static_cast<cudaStream_t>(stream)>>>(q, B, R);
+    P6D_CUDA(cudaGetLastError());
+    return P6D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// p6d_loss.cu -- PoseLoss forward + backward in one launch (sm_100a).
+//
+// Replaces ~20 forward + ~20 autograd-backward eager launches of
+// PoseLoss.forward (reference models/pose_loss.py:19-61) on ~2 KB of data.
+// Per row: normalise both quaternions (x / max(|x|, 1e-12), F.normalize), resolve the
+// double cover, 2*atan2(|q1-q2|, |q1+q2|) or the quaternion-L1 distance, |t_p - t_g|;
+// gradients w.r.t. the prediction are emitted by the same threads (PyTorch's
+// sub-gradient conventions, see oracle/pose_oracle.c p6o_pose_loss).
+//
+// Two shapes of the same kernel:
+//   B <= SMALL_B : one CTA; per-row terms go to shared memory and one warp reduces them
+//                  in ATen's summation order, so the L1 rotation term and the translation
+//                  term equal the CPU reference bit for bit (atan2f differs by <= 2 ulp);
+//   B >  SMALL_B : grid-stride rows, float64 block partials + atomics, last block
+//                  finalises (HBM-bound shape used for the GB/s measurement).
+#include "p6d_common.cuh"
+
+namespace p6d {
+
+constexpr int LOSS_T = 256;
+constexpr int SMALL_B = 2048;
+
+struct Workspace {
+    double rot_sum;
+    double trans_sum;
+    unsigned long long blocks_done;
+    unsigned long long pad;
+};
+
+struct RowOut {
+    float rot;     // per-row rotation term
+    float ad[3];   // |t_p - t_g|
+};
+
+__device__ __forceinline__ float norm4(const float* v) {
+    float s = __fmul_rn(v[0], v[0]);
+    s = __fmaf_rn(v[1], v[1], s);
+    s = __fmaf_rn(v[2], v[2], s);
+    s = __fmaf_rn(v[3], v[3], s);
+    return __fsqrt_rn(s);
+}
+
+__device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* __restrict__ pt,
+                                           const float* __restrict__ gq, const float* __restrict__ gt,
+                                           int64_t b, int64_t B, float wr, float wt, int mode,
+                                           float* __restrict__ grad_q, float* __restrict__ grad_t) {
+    RowOut o;
+    const float4 a4 = *reinterpret_cast<const float4*>(pq + 4 * b);
+    const float4 c4 = *reinterpret_cast<const float4*>(gq + 4 * b);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float c[4] = {c4.x, c4.y, c4.z, c4.w};
+    const float na_raw = norm4(a), nc_raw = norm4(c);
+    const float na = na_raw > 1e-12f ? na_raw : 1e-12f;
+    const float nc = nc_raw > 1e-12f ? nc_raw : 1e-12f;
+    float u[4], v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        u[k] = __fdiv_rn(a[k], na);
+        v[k] = __fdiv_rn(c[k], nc);
+    }
+    double gu[4];
+    if (mode == 0) {
+        float dot = __fmul_rn(u[0], v[0]);
+        dot = __fadd_rn(dot, __fmul_rn(u[1], v[1]));
+        dot = __fadd_rn(dot, __fmul_rn(u[2], v[2]));
+        dot = __fadd_rn(dot, __fmul_rn(u[3], v[3]));
+        if (dot < 0.0f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = -v[k];
+        }
+        float d[4], s[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            d[k] = __fsub_rn(u[k], v[k]);
+            s[k] = __fadd_rn(u[k], v[k]);
+        }
+        const float dn = norm4(d), sn = norm4(s);
+        o.rot = __fmul_rn(2.0f, atan2f(dn, sn));
+        const double den = (double)dn * dn + (double)sn * sn;
+        const double dA_ddn = den > 0.0 ? 2.0 * sn / den : 0.0;
+        const double dA_dsn = den > 0.0 ? -2.0 * dn / den : 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double g = 0.0;
+            if (dn > 0.0f) g += dA_ddn * (double)d[k] / dn;
+            if (sn > 0.0f) g += dA_dsn * (double)s[k] / sn;
+            gu[k] = g;
+        }
+    } else {
+        float ap[4], am[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ap[k] = __fsub_rn(u[k], v[k]);
+            am[k] = __fadd_rn(u[k], v[k]);
+        }
+        float dp = fabsf(ap[0]), dm = fabsf(am[0]);
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            dp = __fadd_rn(dp, fabsf(ap[k]));
+            dm = __fadd_rn(dm, fabsf(am[k]));
+        }
+        o.rot = min_nan(dp, dm);
+        const double wp = dp < dm ? 1.0 : (dp == dm ? 0.5 : 0.0);
+        const double wm = dm < dp ? 1.0 : (dp == dm ? 0.5 : 0.0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double sp = (ap[k] > 0.0f) - (ap[k] < 0.0f);
+            const double sm = (am[k] > 0.0f) - (am[k] < 0.0f);
+            gu[k] = wp * sp + wm * sm;
+        }
+    }
+    if (grad_q) {
+        double gdotu = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gdotu += gu[k] * (double)u[k];
+        const double scale = (double)wr / (double)B;
+        float4 g4;
+        float* gp = reinterpret_cast<float*>(&g4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double g;
+            if (na_raw >= 1e-12f && na_raw > 0.0f) g = (gu[k] - (double)u[k] * gdotu) / (double)na;
+            else g = gu[k] / (double)na;
+            gp[k] = (float)(scale * g);
+        }
+        *reinterpret_cast<float4*>(grad_q + 4 * b) = g4;
+    }
+    const double tscale = (double)wt / (3.0 * (double)B);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float df = __fsub_rn(pt[3 * b + k], gt[3 * b + k]);
+        o.ad[k] = fabsf(df);
+        if (grad_t) {
+            const double sg = (df > 0.0f) - (df < 0.0f);
+            grad_t[3 * b + k] = (float)(tscale * sg);
+        }
+    }
+    return o;
+}
+
+__device__ __forceinline__ void finish(float rot, float tr, float wr, float wt, float* out) {
+    out[0] = __fadd_rn(__fmul_rn(wr, rot), __fmul_rn(wt, tr));
+    out[1] = rot;
+    out[2] = tr;
+}
+
+// B <= SMALL_B: single CTA, ATen-ordered means
+__global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq, const float* pt, const float* gq,
+                                                                 const float* gt, int B, float wr, float wt,
+                                                                 int mode, float* out, float* grad_q,
+                                                                 float* grad_t) {
+    __shared__ float s_rot[SMALL_B];
+    __shared__ float s_ad[3 * SMALL_B];
+    for (int b = threadIdx.x; b < B; b += LOSS_T) {
+        const RowOut o = loss_row(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t);
+        s_rot[b] = o.rot;
+        s_ad[3 * b] = o.ad[0];
+        s_ad[3 * b + 1] = o.ad[1];
+        s_ad[3 * b + 2] = o.ad[2];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const float rot = aten_mean_warp([&](int e) { return s_rot[e]; }, B, lane);
+        const float tr = aten_mean_warp([&](int e) { return s_ad[e]; }, 3 * B, lane);
+        if (lane == 0) finish(rot, tr, wr, wt, out);
+    }
+}
+
+// B > SMALL_B: grid-stride, float64 partial sums, last block finalises
+__global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq, const float* pt, const float* gq,
+                                                                 const float* gt, int64_t B, float wr, float wt,
+                                                                 int mode, float* out, float* grad_q,
+                                                                 float* grad_t, Workspace* ws) {
+    double rs = 0.0, ts = 0.0;
+    for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * LOSS_T) {
+        const RowOut o = loss_row(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t);
+        rs += (double)o.rot;
+        ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+    }
+    __shared__ double s_r[LOSS_T / 32], s_t[LOSS_T / 32];
+    __shared__ bool s_last;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_r[w] = rs; s_t[w] = ts; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0, t = 0.0;
+        for (int i = 0; i < LOSS_T / 32; ++i) { r += s_r[i]; t += s_t[i]; }
+        atomicAdd(&ws->rot_sum, r);
+        atomicAdd(&ws->trans_sum, t);
+        __threadfence();
+        const unsigned long long done = atomicAdd(&ws->blocks_done, 1ull);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        __threadfence();
+        const double r = atomicAdd(&ws->rot_sum, 0.0), t = atomicAdd(&ws->trans_sum, 0.0);
+        finish((float)(r / (double)B), (float)(t / (3.0 * (double)B)), wr, wt, out);
+        ws->rot_sum = 0.0;  // leave the workspace zeroed for the next call
+        ws->trans_sum = 0.0;
+        ws->blocks_done = 0ull;
+    }
+}
+
+}  // namespace p6d
+
+using namespace p6d;
+
+extern "C" {
+
+int64_t p6d_pose_loss_workspace_bytes(void) { return (int64_t)sizeof(Workspace); }
+
+int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, const float* gt, int64_t B,
+                          float rot_weight, float trans_weight, int mode, float* out, float* grad_q,
+                          float* grad_t, void* workspace, int device, void* stream) {
+    if (B <= 0 || !pq || !pt || !gq || !gt || !out || (mode != 0 && mode != 1)) {
+        set_error("p6d_pose_loss_fwd_bwd: bad arguments (B=%lld, mode=%d)", (long long)B, mode);
+        return P6D_EINVAL;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (B <= SMALL_B) {
+        pose_loss_small_kernel<<<1, LOSS_T, 0, st>>>(pq, pt, gq, gt, (int)B, rot_weight, trans_weight, mode, out,
+                                                     grad_q, grad_t);
+    } else {
+        if (!workspace) { set_error("p6d_pose_loss_fwd_bwd: workspace required for B > %d", SMALL_B); return P6D_EINVAL; }
+        int sms = 0;
+        P6D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        int64_t blocks = (B + LOSS_T - 1) / LOSS_T;
+        const int64_t cap = (int64_t)sms * 8;
+        if (blocks > cap) blocks = cap;
+        pose_loss_large_kernel<<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
+                                                                    mode, out, grad_q, grad_t,
+                                                                    static_cast<Workspace*>(workspace));
+    }
+    P6D_CUDA(cudaGetLastError());
+    return P6D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+// p6d_peak.cu -- FP32 issue-rate microbenchmarks (measurement helper, sm_100a).
+//
+// MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only; the ADD-S kernel is bound by
+// the FP32 FMA pipe, so its roofline needs a measured FP32 denominator as well:
+//   kind 0  FFMA  : 16 independent scalar FMA chains per thread
+//   kind 1  FFMA2 : 16 independent packed (f32x2) FMA chains per thread
+//   kind 2  MIX   : the ADD-S inner tile (3 FADD2 + FMUL2 + 2 FFMA2 + FMNMX3 per two pairs)
+//                   on register operands, no shared-memory traffic
+// FLOP accounting: FMA = 2 FLOP per lane-op; MIX = 8 FLOP per pair (3 sub, 3 mul, 2 add),
+// the same convention as the kernel's algorithmic FLOPs.
+#include "p6d_common.cuh"
+
+namespace p6d {
+
+constexpr int PK_T = 256;
+constexpr int PK_CHAINS = 16;
+constexpr int PK_INNER = 64;
+
+__global__ void __launch_bounds__(PK_T) peak_ffma_kernel(float* out, int iters, float a, float b) {
+    float v[PK_CHAINS];
+#pragma unroll
+    for (int i = 0; i < PK_CHAINS; ++i) v[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < PK_INNER; ++j) {
+#pragma unroll
+            for (int i = 0; i < PK_CHAINS; ++i) v[i] = __fmaf_rn(v[i], a, b);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PK_CHAINS; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(PK_T) peak_ffma2_kernel(float* out, int iters, float a, float b) {
+    float2 v[PK_CHAINS];
+#pragma unroll
+    for (int i = 0; i < PK_CHAINS; ++i) v[i] = make_float2(threadIdx.x * 1e-3f + i, i - threadIdx.x * 1e-3f);
+    const float2 aa = make_float2(a, a * 1.0001f), bb = make_float2(b, b * 0.999f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < PK_INNER; ++j) {
+#pragma unroll
+            for (int i = 0; i < PK_CHAINS; ++i) v[i] = fma2(v[i], aa, bb);
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PK_CHAINS; ++i) s += v[i].x + v[i].y;
+    if (s == 123.456f) out[0] = s;
+}
+
+constexpr int MIX_K = 8;
+__global__ void __launch_bounds__(PK_T, 2) peak_mix_kernel(float* out, int iters, float g0) {
+    float px[MIX_K], py[MIX_K], pz[MIX_K], m[MIX_K];
+#pragma unroll
+    for (int k = 0; k < MIX_K; ++k) {
+        px[k] = threadIdx.x * 1e-3f + k;
+        py[k] = k * 0.5f - threadIdx.x * 1e-3f;
+        pz[k] = 0.25f * k;
+        m[k] = 3.0e38f;
+    }
+    float2 gx = make_float2(g0, g0 + 1.0f), gy = make_float2(g0 * 0.5f, g0 - 1.0f), gz = make_float2(-g0, 2.0f * g0);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int k = 0; k < MIX_K; ++k) {
+                const float2 dx = sub2(make_float2(px[k], px[k]), gx);
+                const float2 dy = sub2(make_float2(py[k], py[k]), gy);
+                const float2 dz = sub2(make_float2(pz[k], pz[k]), gz);
+                float2 s = mul2(dx, dx);
+                s = fma2(dy, dy, s);
+                s = fma2(dz, dz, s);
+                m[k] = min3_nan(m[k], s.x, s.y);
+            }
+            // change the "gt" operands so nothing is hoisted (2 extra scalar adds per 16 pairs)
+            gx.x += 1.0f;
+            gy.y -= 1.0f;
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < MIX_K; ++k) s += m[k];
+    if (s == 123.456f) out[0] = s;
+}
+
+}  // namespace p6d
+
+using namespace p6d;
+
+extern "C" int p6d_fp32_microbench(int kind, int device, int iters, double* tflops, double* ms) {
+    if (kind < 0 || kind > 2 || iters < 1 || !tflops || !ms) { set_error("p6d_fp32_microbench: bad arguments"); return P6D_EINVAL; }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    int sms = 0;
+    P6D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float* d_out = nullptr;
+    P6D_CUDA(cudaMalloc(&d_out, 64));
+    cudaEvent_t e0, e1;
+    P6D_CUDA(cudaEventCreate(&e0));
+    P6D_CUDA(cudaEventCreate(&e1));
+    const int per_sm = (kind == 2) ? 2 : 4;
+    const unsigned grid = (unsigned)(sms * per_sm);
+    auto launch = [&](int n) {
+        if (kind == 0) peak_ffma_kernel<<<grid, PK_T>>>(d_out, n, 1.0001f, 0.5f);
+        else if (kind == 1) peak_ffma2_kernel<<<grid, PK_T>>>(d_out, n, 1.0001f, 0.5f);
+        else peak_mix_kernel<<<grid, PK_T>>>(d_out, n, 0.125f);
+    };
+    launch(iters / 4 + 1);  // warm-up
+    P6D_CUDA(cudaDeviceSynchronize());
+    P6D_CUDA(cudaEventRecord(e0));
+    launch(iters);
+    P6D_CUDA(cudaEventRecord(e1));
+    P6D_CUDA(cudaEventSynchronize(e1));
+    float t = 0.0f;
+    P6D_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    P6D_CUDA(cudaGetLastError());
+    const double threads = (double)grid * PK_T;
+    double flop;
+    if (kind == 0) flop = threads * iters * (double)PK_INNER * PK_CHAINS * 2.0;
+    else if (kind == 1) flop = threads * iters * (double)PK_INNER * PK_CHAINS * 4.0;
+    else flop = threads * iters * 8.0 * MIX_K * 2.0 /*pairs per tile*/ * 8.0 /*FLOP per pair*/;
+    *ms = t;
+    *tflops = flop / (t * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    return P6D_OK;
+}

@@ -1,0 +1,254 @@
+"""ADD / ADD-S / ADD-0.1d on B200 -- drop-in for the reference's ``models/add_loss.py``.
+
+Same names, argument order, defaults and return types as the reference
+(SFR-Vision/6d-pose-estimation ``models/add_loss.py``); the arithmetic runs in
+``libp6d.so`` (hand-written sm_100a kernels) instead of a per-pose Python loop of eager
+ops.  One kernel launch and one device->host copy per ``eval_metrics`` call replace
+~12 launches and 4 host syncs per pose (reference ``add_loss.py:168-195``).
+
+There is no CPU path: the device must be CUDA.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def _core():
+    mod = sys.modules.get("p6d_b200_core")
+    if mod is None:
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location("p6d_b200_bootstrap", os.path.join(here, "_bootstrap.py"))
+        boot = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(boot)
+        mod = boot.core()
+    return mod
+
+
+# eggbox and glue (reference add_loss.py:10)
+SYMMETRIC_OBJECT_IDS = {9, 10}
+
+_SORT_THRESHOLD = 256  # batches at least this large are processed in object order
+
+
+def _read_ascii_ply(path):
+    """Vertex block of an ASCII PLY, with the reference's permissive rule
+    (add_loss.py:83-99): after the header every line with >= 3 whitespace-separated
+    tokens contributes its first three as a vertex -- face lines ``3 i j k`` included."""
+    rows = []
+    with open(path, "r") as fh:
+        in_body = False
+        for raw in fh:
+            if not in_body:
+                in_body = "end_header" in raw
+                continue
+            tok = raw.split()
+            if len(tok) >= 3:
+                rows.append((float(tok[0]), float(tok[1]), float(tok[2])))
+    return np.array(rows)
+
+
+class _AddForward(torch.autograd.Function):
+    """Attaches the fused backward (p6d_add_backward) to an already computed loss value."""
+
+    @staticmethod
+    def forward(ctx, value, crit, saved, pred_r, pred_t):
+        ctx.crit, ctx.saved = crit, saved
+        ctx.shapes = (pred_r.shape, pred_t.shape, pred_r.dtype, pred_t.dtype)
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gq, gt = ctx.crit._forward_grads(ctx.saved, grad_out)
+        rs, ts, rd, td = ctx.shapes
+        return None, None, None, gq.reshape(rs).to(rd), gt.reshape(ts).to(td)
+
+
+class ADDLoss(nn.Module):
+    """ADD, ADD-S and ADD-0.1d for 6-D pose estimation (reference add_loss.py:13-215)."""
+
+    def __init__(self, model_dir, device, rot_weight=0.0, trans_weight=0.0):
+        super().__init__()
+        self.points = {}       # object id -> float32 [N,3] tensor on `device`
+        self.diameters = {}    # object id -> metres
+        self.device = device
+        self.rot_weight = rot_weight      # stored, unused -- as in the reference (:24-25)
+        self.trans_weight = trans_weight
+        self._table = None
+        self._table_key = None
+        self._load_models(model_dir)
+
+    # ------------------------------------------------------------------ loading
+    def _load_ply(self, path):
+        return _read_ascii_ply(path)
+
+    def _load_models(self, model_dir, num_points=500):
+        """PLY meshes + diameters.  Consumes the global NumPy RNG exactly like the
+        reference (diameter-fallback ``choice`` first, then the down-sampling ``choice``,
+        per PLY in sorted order; add_loss.py:29-81) so a fixed ``np.random.seed`` gives
+        the same 500-point subsets."""
+        known = {}
+        info_file = os.path.join(model_dir, "models_info.yml")
+        if os.path.exists(info_file):
+            import yaml
+            with open(info_file, "r") as fh:
+                info = yaml.safe_load(fh)
+            for key, entry in info.items():
+                try:
+                    if "diameter" in entry:
+                        known[int(key) - 1] = entry["diameter"] / 1000.0
+                except Exception:
+                    continue
+        for name in sorted(n for n in os.listdir(model_dir) if n.endswith(".ply")):
+            try:
+                oid = int(name.split("_")[1].split(".")[0]) - 1
+            except Exception:
+                continue
+            cloud = self._load_ply(os.path.join(model_dir, name)) / 1000.0
+            cloud = cloud[np.linalg.norm(cloud, axis=1) < 0.5]      # outlier filter (:61-62)
+            if oid in known:
+                self.diameters[oid] = known[oid]
+            elif cloud.shape[0] > 10:
+                pick = np.random.choice(cloud.shape[0], min(100, cloud.shape[0]), replace=False)
+                sub = cloud[pick]
+                self.diameters[oid] = np.max(np.linalg.norm(sub[:, None] - sub[None, :], axis=2))
+            else:
+                self.diameters[oid] = 0.1
+            if cloud.shape[0] > num_points:
+                cloud = cloud[np.random.choice(cloud.shape[0], num_points, replace=False)]
+            self.points[oid] = torch.from_numpy(cloud.astype(np.float32)).to(self.device)
+
+    # ------------------------------------------------------------------ device table
+    def _cuda_device(self, like=None):
+        core = _core()
+        dev = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        if dev.type != "cuda" and like is not None and like.is_cuda:
+            dev = like.device
+        return core.require_cuda(dev)
+
+    def _mesh_table(self, device):
+        """(Re)build the device mesh table when points / diameters were mutated."""
+        key = (str(device),) + tuple(
+            (k, v.data_ptr(), v._version, tuple(v.shape)) if isinstance(v, torch.Tensor)
+            else (k, id(v)) for k, v in sorted(self.points.items())
+        ) + tuple(sorted((k, float(v)) for k, v in self.diameters.items()))
+        if self._table is None or key != self._table_key:
+            if self._table is not None:
+                self._table.close()
+            self._table = _core().MeshTable(self.points, self.diameters, SYMMETRIC_OBJECT_IDS, device)
+            self._table_key = key
+        return self._table
+
+    def _prepare(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+        core = _core()
+        dev = self._cuda_device(pred_r if isinstance(pred_r, torch.Tensor) else None)
+        pq = core.as_cuda_f32(pred_r, dev, (4,))
+        pt = core.as_cuda_f32(pred_t, dev, (3,))
+        gq = core.as_cuda_f32(gt_r, dev, (4,))
+        gt = core.as_cuda_f32(gt_t, dev, (3,))
+        obj = obj_ids if isinstance(obj_ids, torch.Tensor) else torch.as_tensor(np.asarray(obj_ids))
+        obj = obj.detach().to(dev, torch.int64, non_blocking=True).reshape(-1).contiguous()
+        B = obj.shape[0]
+        if not (pq.shape[0] == pt.shape[0] == gq.shape[0] == gt.shape[0] == B):
+            raise ValueError("pred_r, pred_t, gt_r, gt_t and obj_ids must share the batch dimension")
+        order = None
+        if B >= _SORT_THRESHOLD:
+            order = torch.argsort(obj, stable=True).to(torch.int32)
+        return dev, pq, pt, gq, gt, obj, order
+
+    # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def eval_metrics(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+        """{'add_mean' [mm], 'add_s_mean' [mm], 'add_01d_acc' [%]} over the poses whose
+        object has a mesh; int 0 entries when there is none (reference :156-201)."""
+        per_pose = self.eval_poses(pred_r, pred_t, gt_r, gt_t, obj_ids)
+        keep = per_pose["valid"].astype(bool)
+        if not keep.any():
+            return {"add_mean": 0, "add_s_mean": 0, "add_01d_acc": 0}
+        # the reference averages Python floats on the host: float64 np.mean
+        return {
+            "add_mean": np.mean(per_pose["add"][keep].astype(np.float64)) * 1000,
+            "add_s_mean": np.mean(per_pose["add_s"][keep].astype(np.float64)) * 1000,
+            "add_01d_acc": np.mean(per_pose["hit"][keep].astype(np.float64)) * 100,
+        }
+
+    @torch.no_grad()
+    def eval_poses(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+        """Per-pose float32 ADD, ADD-S, uint8 hit / valid as NumPy arrays (one launch,
+        one device->host copy).  Addition to the reference surface."""
+        dev, pq, pt, gq, gt, obj, order = self._prepare(pred_r, pred_t, gt_r, gt_t, obj_ids)
+        B = obj.shape[0]
+        if B == 0 or not self.points:
+            z = np.zeros(B, np.float32)
+            return {"add": z, "add_s": z.copy(), "hit": np.zeros(B, np.uint8), "valid": np.zeros(B, np.uint8)}
+        table = self._mesh_table(dev)
+        _, _, _, _, packed = table.evaluate(pq, pt, gq, gt, obj, True, order)
+        host = packed.cpu().numpy()       # the only synchronisation of the call
+        return {"add": host[:4 * B].view(np.float32), "add_s": host[4 * B:8 * B].view(np.float32),
+                "hit": host[8 * B:9 * B], "valid": host[9 * B:10 * B]}
+
+    # ------------------------------------------------------------------ differentiable loss
+    def forward(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+        """Mean over valid samples of ADD (asymmetric ids) or ADD-S (symmetric ids);
+        0-d tensor; a ``requires_grad`` zero when no sample has a mesh (reference :101-150)."""
+        value, saved = self._forward_value(pred_r, pred_t, gt_r, gt_t, obj_ids)
+        if saved is None:
+            return value
+        wants_grad = torch.is_grad_enabled() and any(
+            isinstance(t, torch.Tensor) and t.requires_grad for t in (pred_r, pred_t))
+        if not wants_grad:
+            return value
+        return _AddForward.apply(value, self, saved, pred_r, pred_t)
+
+    def train_loss(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+        return self.forward(pred_r, pred_t, gt_r, gt_t, obj_ids)
+
+    @torch.no_grad()
+    def _forward_value(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+        dev, pq, pt, gq, gt, obj, order = self._prepare(pred_r, pred_t, gt_r, gt_t, obj_ids)
+        B = obj.shape[0]
+        if B == 0 or not self.points:
+            return torch.tensor(0.0, device=dev).requires_grad_(True), None
+        table = self._mesh_table(dev)
+        add, adds, _, valid, _ = table.evaluate(pq, pt, gq, gt, obj, True, order)
+        sym = torch.from_numpy(table.symmetric.astype(np.bool_)).to(dev)
+        in_range = (obj >= 0) & (obj < table.n_slots)
+        is_sym = torch.zeros(B, dtype=torch.bool, device=dev)
+        is_sym[in_range] = sym[obj[in_range]]
+        per_sample = torch.where(is_sym, adds, add)
+        keep = valid.bool()
+        count = int(keep.sum().item())
+        if count == 0:
+            return torch.tensor(0.0, device=dev).requires_grad_(True), None
+        # the reference sums per object group (first-appearance order) in float32
+        total = torch.zeros((), dtype=torch.float32, device=dev)
+        seen = []
+        for o in obj[keep].tolist():
+            if o not in seen:
+                seen.append(o)
+        for o in seen:
+            total = total + per_sample[keep & (obj == o)].sum()
+        saved = (pq, pt, gq, gt, obj, is_sym, keep, count, table, dev)
+        return total / count, saved
+
+    def _forward_grads(self, saved, grad_out):
+        core = _core()
+        if saved is None:
+            return None, None
+        if not hasattr(core.lib(), "p6d_add_backward"):
+            raise NotImplementedError("gradient of ADDLoss.forward needs p6d_add_backward (SURVEY.md N3)")
+        return core.add_backward(saved, grad_out)
+
+    # ------------------------------------------------------------------ quaternion -> matrix
+    def _quat_to_mat(self, q):
+        """[B,4] scalar-last quaternions -> [B,3,3]; no normalisation (reference :203-215)."""
+        core = _core()
+        dev = self._cuda_device(q if isinstance(q, torch.Tensor) else None)
+        qq = core.as_cuda_f32(q, dev, (4,))
+        out = torch.empty(qq.shape[0], 3, 3, dtype=torch.float32, device=dev)
+        core.check(core.lib().p6d_quat_to_mat(core.ptr(qq), qq.shape[0], core.ptr(out), dev.index,
+                                              core.stream_ptr(dev)))
+        return out

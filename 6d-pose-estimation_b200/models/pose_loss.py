@@ -1,0 +1,107 @@
+"""Geodesic / quaternion-L1 rotation loss + L1 translation loss on B200 -- drop-in for
+the reference's ``models/pose_loss.py`` (SFR-Vision/6d-pose-estimation).
+
+``PoseLoss.forward`` returns the same 0-d tensor as the reference and supports
+``.backward()``; the forward value and the gradients w.r.t. the predictions come out of
+ONE kernel launch (``p6d_pose_loss_fwd_bwd``) instead of ~40 eager launches
+(reference ``pose_loss.py:19-61`` + autograd).  CUDA only, no CPU path.
+"""
+import importlib.util
+import os
+import sys
+
+import torch
+import torch.nn as nn
+
+
+def _core():
+    mod = sys.modules.get("p6d_b200_core")
+    if mod is None:
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location("p6d_b200_bootstrap", os.path.join(here, "_bootstrap.py"))
+        boot = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(boot)
+        mod = boot.core()
+    return mod
+
+
+_workspaces = {}
+
+
+def _workspace(dev):
+    ws = _workspaces.get(dev)
+    if ws is None:
+        ws = torch.zeros(int(_core().lib().p6d_pose_loss_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _workspaces[dev] = ws
+    return ws
+
+
+class _FusedPoseLoss(torch.autograd.Function):
+    """out = [loss, rot_term, trans_term]; grads for upstream 1 are produced by the
+    forward launch and scaled by grad_output in backward."""
+
+    @staticmethod
+    def forward(ctx, pred_rot, pred_trans, gt_rot, gt_trans, rot_weight, trans_weight, mode, pick):
+        core = _core()
+        dev = core.require_cuda(pred_rot.device)
+        pq = core.as_cuda_f32(pred_rot, dev, (4,))
+        pt = core.as_cuda_f32(pred_trans, dev, (3,))
+        gq = core.as_cuda_f32(gt_rot, dev, (4,))
+        gt = core.as_cuda_f32(gt_trans, dev, (3,))
+        B = pq.shape[0]
+        if not (pt.shape[0] == gq.shape[0] == gt.shape[0] == B) or B == 0:
+            raise ValueError("PoseLoss needs non-empty inputs with a common batch dimension")
+        need_q = ctx.needs_input_grad[0]
+        need_t = ctx.needs_input_grad[1]
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        gq_out = torch.empty_like(pq) if need_q else None
+        gt_out = torch.empty_like(pt) if need_t else None
+        core.check(core.lib().p6d_pose_loss_fwd_bwd(
+            core.ptr(pq), core.ptr(pt), core.ptr(gq), core.ptr(gt), B, float(rot_weight), float(trans_weight),
+            int(mode), core.ptr(out), core.ptr(gq_out), core.ptr(gt_out), core.ptr(_workspace(dev)),
+            dev.index, core.stream_ptr(dev)))
+        ctx.grads = (gq_out, gt_out)
+        ctx.meta = (pred_rot.shape, pred_trans.shape, pred_rot.dtype, pred_trans.dtype, pick)
+        return out[pick].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        gq, gt = ctx.grads
+        rs, ts, rd, td, pick = ctx.meta
+        # pick 0: d loss; pick 1: d rot_term (the kernel ran with rot_weight 1, trans_weight 0)
+        dq = (gq * grad_out).reshape(rs).to(rd) if gq is not None else None
+        dt = (gt * grad_out).reshape(ts).to(td) if gt is not None else None
+        return dq, dt, None, None, None, None, None, None
+
+
+class PoseLoss(nn.Module):
+    """rot_weight * rotation_loss + trans_weight * L1(translation)  (reference :8-65)."""
+
+    def __init__(self, rot_weight=1.0, trans_weight=1.0, rotation_loss='geodesic'):
+        super().__init__()
+        self.rot_weight = rot_weight
+        self.trans_weight = trans_weight
+        self.rotation_loss_type = rotation_loss
+
+    def _mode(self):
+        # anything other than 'geodesic' selects the quaternion-L1 distance (reference :21-24)
+        return 0 if self.rotation_loss_type == 'geodesic' else 1
+
+    def forward(self, pred_rot, pred_trans, gt_rot, gt_trans, obj_ids=None):
+        return _FusedPoseLoss.apply(pred_rot, pred_trans, gt_rot, gt_trans, self.rot_weight,
+                                    self.trans_weight, self._mode(), 0)
+
+    def _rotation_only(self, q1, q2, mode):
+        zeros = torch.zeros(q1.shape[0], 3, dtype=torch.float32, device=q1.device)
+        return _FusedPoseLoss.apply(q1, zeros, q2, zeros, 1.0, 0.0, mode, 1)
+
+    def _geodesic_distance(self, q1, q2):
+        """mean_b 2*atan2(|q1-q2'|, |q1+q2'|) on normalised quaternions (reference :30-50)."""
+        return self._rotation_only(q1, q2, 0)
+
+    def _quaternion_l1(self, q1, q2):
+        """mean_b min(sum|q1-q2|, sum|q1+q2|) on normalised quaternions (reference :52-61)."""
+        return self._rotation_only(q1, q2, 1)
+
+    def train_loss(self, pred_rot, pred_trans, gt_rot, gt_trans, obj_ids=None):
+        return self.forward(pred_rot, pred_trans, gt_rot, gt_trans, obj_ids)

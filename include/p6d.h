@@ -1,0 +1,161 @@
+/*
+ * p6d.h -- C ABI of libp6d.so, the B200 (sm_100a) pose-geometry library.
+ *
+ * The reference (SFR-Vision/6d-pose-estimation) is pure Python and has no FFI of its
+ * own; the drop-in boundary is the Python call surface of models/add_loss.py,
+ * models/pose_loss.py and utils/camera.py.  Each entry point below
+ * names the reference code it replaces; the ctypes binding a maintainer would add is in
+ * INTEGRATION.md and lives in 6d-pose-estimation_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in the signatures
+ *     (`stream` is a cudaStream_t passed as void*, NULL = legacy default stream);
+ *   - every function returns 0 on success and a negative P6D_E* code on failure;
+ *     p6d_last_error() returns the thread-local message of the last failure;
+ *   - unless the name ends in _host, data pointers are DEVICE pointers on the device the
+ *     mesh table (or, for table-less calls, the `device` argument) belongs to, float32
+ *     contiguous, quaternions scalar-last [x,y,z,w], translations in metres, K row-major
+ *     3x3; the caller owns every buffer;
+ *   - there is no CPU fallback: without a CUDA device every compute entry fails with
+ *     P6D_ECUDA.
+ */
+#ifndef P6D_H_
+#define P6D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define P6D_VERSION 1
+
+#define P6D_OK 0
+#define P6D_EINVAL (-1)   /* bad argument */
+#define P6D_ECUDA (-2)    /* CUDA runtime error (message has the CUDA string) */
+#define P6D_ENOMEM (-3)   /* host or device allocation failed */
+#define P6D_ETOOBIG (-4)  /* mesh does not fit the shared-memory budget of the kernel */
+
+int p6d_version(void);
+const char* p6d_last_error(void);
+
+/* Device facts used by the host side to size grids / report rooflines. */
+int p6d_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz,
+                    int64_t* smem_per_block_optin);
+
+/* ---------------------------------------------------------------------------------------
+ * Mesh table: device-resident copy of ADDLoss.points / ADDLoss.diameters
+ * (reference: models/add_loss.py:21-22, filled by _load_models :29-81).
+ *   xyz        host, row-major [sum counts, 3] float32, objects back to back
+ *   offsets    host [n_slots] first point of object id s
+ *   counts     host [n_slots] point count, 0 = id not in self.points (poses with that id
+ *              are skipped, add_loss.py:171-172)
+ *   diameters  host [n_slots] metres, float64; threshold = 0.1 * diameter in float64 (:176)
+ *   symmetric  host [n_slots] 1 for ids in SYMMETRIC_OBJECT_IDS (:10)
+ * The table stores each mesh as a 16-byte aligned SoA block x[Np] y[Np] z[Np]
+ * (Np = count rounded up to 4) so one TMA bulk copy stages it into shared memory.
+ * ------------------------------------------------------------------------------------- */
+typedef struct p6d_mesh_table p6d_mesh_table;
+
+int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_t* counts,
+                          const double* diameters, const uint8_t* symmetric, int n_slots, int device,
+                          p6d_mesh_table** out);
+int p6d_mesh_table_destroy(p6d_mesh_table* table);
+/* Largest mesh (points) the ADD-S kernel accepts on this device. */
+int p6d_adds_max_points(int device, int* max_points);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-pose evaluation = the loop body of ADDLoss.eval_metrics (models/add_loss.py:168-195)
+ * for B poses in one launch.
+ *   pq,gq [B,4]  pt,gt [B,3]  obj [B] int64
+ *   order        nullable [B] int32: processing order (e.g. argsort of obj so consecutive
+ *                poses share a mesh); outputs are still written at the original index
+ *   add  [B]     mean_i |pred_i - gt_i|                       (:181-183)
+ *   adds [B]     mean_i min_j |pred_i - gt_j|, pred-major      (:185-190); NULL = skip the
+ *                all-pairs part (ADD-only kernel, symmetric ids then decide on ADD)
+ *   hit  [B]     (double)(symmetric ? adds : add) < 0.1*diameter  (:192-195)
+ *   valid[B]     0 where the object id has no mesh (outputs 0 there)
+ *   acc          nullable per-object accumulators updated with atomics (not zeroed here):
+ *                hits[n_slots], valid[n_slots] int64; add_sum[n_slots], adds_sum[n_slots]
+ *                float64 (any of the four pointers may be NULL)
+ * Distances reproduce the reference's float32 arithmetic bit for bit, including the
+ * summation order of Tensor.mean() on the CPU.
+ * ------------------------------------------------------------------------------------- */
+typedef struct p6d_accumulators {
+    int64_t* hits;
+    int64_t* valid;
+    double* add_sum;
+    double* adds_sum;
+} p6d_accumulators;
+
+int p6d_add_eval(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                 const float* gt, const int64_t* obj, const int32_t* order, int64_t B, float* add,
+                 float* adds, uint8_t* hit, uint8_t* valid, const p6d_accumulators* acc,
+                 void* stream);
+
+/* Same computation with HOST buffers: stages inputs to the device, runs the kernels,
+ * copies results back and synchronises (the end-to-end path of bench.py).  acc_* are
+ * host arrays [n_slots] that receive (not accumulate) the per-object totals; nullable.
+ * gpu_launches (nullable) receives the number of kernels this call launched. */
+int p6d_add_eval_host(p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                      const float* gt, const int64_t* obj, int64_t B, int want_adds, float* add,
+                      float* adds, uint8_t* hit, uint8_t* valid, int64_t* acc_hits,
+                      int64_t* acc_valid, double* acc_add_sum, double* acc_adds_sum,
+                      int* gpu_launches);
+
+/* Quaternion -> rotation matrix, ADDLoss._quat_to_mat (models/add_loss.py:203-215). */
+int p6d_quat_to_mat(const float* q, int64_t B, float* R, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * PoseLoss.forward + gradients in one launch (models/pose_loss.py:19-61).
+ *   mode 0 = 'geodesic' (:30-50), 1 = quaternion L1 (:52-61)
+ *   out[0] = loss, out[1] = rotation term, out[2] = translation term (float32)
+ *   grad_q [B,4], grad_t [B,3]: d loss / d pred for upstream gradient 1 (nullable)
+ *   workspace: device buffer of p6d_pose_loss_workspace_bytes() bytes, zeroed by the
+ *   caller before the first use only (the kernel leaves it zeroed).
+ * ------------------------------------------------------------------------------------- */
+int64_t p6d_pose_loss_workspace_bytes(void);
+int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, const float* gt,
+                          int64_t B, float rot_weight, float trans_weight, int mode, float* out,
+                          float* grad_q, float* grad_t, void* workspace, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Pinhole XY from bbox centre and predicted Z
+ * (PoseNetRGBGeometric._compute_pinhole_translation, models/pose_net_rgb_geometric.py:93-109).
+ *   z [B], uv [B,2], K [3,3] (k_batched = 0) or [B,3,3]; out [B,3] = (((u-cx)*z)/fx, ..., z)
+ * Backward: grad_z [B] = gx*(u-cx)/fx + gy*(v-cy)/fy + gz for grad_out [B,3].
+ * ------------------------------------------------------------------------------------- */
+int p6d_pinhole_fwd(const float* z, const float* uv, const float* K, int k_batched, int64_t B,
+                    float* out, int device, void* stream);
+int p6d_pinhole_bwd(const float* grad_out, const float* uv, const float* K, int k_batched, int64_t B,
+                    float* grad_z, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Depth sample + back-projection
+ * (PoseNetRGBDGeometric._compute_pinhole_translation, models/pose_net_rgbd_geometric.py:56-85).
+ *   depth [B,H,W] metres; centre clamped to [0,clamp_hi] (reference: 223), truncated for
+ *   the index; z <= 0.01 or NaN -> 0.5; clamp [0.1, 2.0]; pinhole XYZ.  out [B,3].
+ * ------------------------------------------------------------------------------------- */
+int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, const float* K,
+                          int k_batched, int64_t B, float clamp_hi, float* out, int device,
+                          void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Measurement helper (no reference counterpart): FP32 issue-rate microbenchmarks that give
+ * the roofline its measured denominator.  kind 0 = FFMA only, 1 = packed FFMA2 only,
+ * 2 = the ADD-S instruction mix (3 FADD2 + FMUL2 + 2 FFMA2 + FMNMX3 per 2 pairs).
+ * Returns achieved TFLOP/s (2 FLOP per FMA lane-op; mix counted as 8 FLOP per pair) and
+ * the kernel time in ms.
+ * ------------------------------------------------------------------------------------- */
+int p6d_fp32_microbench(int kind, int device, int iters, double* tflops, double* ms);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* P6D_H_ */

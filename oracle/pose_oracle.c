@@ -23,7 +23,7 @@
  *     256-bit vectors (8 lanes) x 4-way ILP x 4 cascade levels of 16 (see aten_sum);
  *   - the ADD-0.1d compare happens in float64 (Python floats).
  *
- * Build: gcc -O2 -fPIC -shared -ffp-contract=off -fno-fast-math -pthread (see Makefile).
+ * Build: gcc -O3 -mavx2 -mfma -fPIC -shared -ffp-contract=off -fno-fast-math -pthread (see Makefile).
  * -ffp-contract=off matters: GCC must not fuse a*b+c on its own.
  */
 #include <math.h>

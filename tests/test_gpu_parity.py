@@ -1,0 +1,307 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes -> libp6d.so), against
+the CPU oracle on the same seeded inputs and against the committed golden vectors that
+came from the reference itself.
+
+Bars (BASELINE.json north-star): ADD-0.1d decisions and per-object accuracy bit-exact;
+distances and loss within 1e-5 relative.  Distances are in fact checked for bit equality
+(the kernels reproduce the reference's float32 rounding and summation order); the
+transcendental loss is checked at 1e-5.
+"""
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits, golden_meshes, load_golden, same_bits
+
+pytestmark = pytest.mark.gpu
+
+EVAL_CASES = ["eval_cfg1", "eval_cfg1_mixed", "eval_cfg2_subset", "eval_ragged", "eval_default_diameter",
+              "eval_degenerate"]
+
+
+def make_crit(pkg, pts, dia, dev):
+    crit = pkg.ADDLoss(tempfile.mkdtemp(), dev)
+    for k, v in pts.items():
+        crit.points[k] = torch.from_numpy(np.ascontiguousarray(v)).to(dev)
+    crit.diameters.update(dia)
+    return crit
+
+
+def T(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def test_native_library_is_loaded(pkg, cuda_dev):
+    info = pkg.core.device_info(cuda_dev.index)
+    assert info["cc"][0] >= 10, f"sm_100a cubin only; device is sm_{info['cc'][0]}{info['cc'][1]}"
+    assert any("libp6d.so" in l for l in open("/proc/self/maps"))
+
+
+def test_quat_to_mat(pkg, cuda_dev):
+    g = load_golden("quat_to_mat")
+    crit = pkg.ADDLoss(tempfile.mkdtemp(), cuda_dev)
+    R = crit._quat_to_mat(T(g["q"], cuda_dev))
+    assert R.shape == (64, 3, 3) and R.device == cuda_dev
+    assert same_bits(R.cpu().numpy(), g["R"])
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_eval_matches_reference_golden(pkg, cuda_dev, name):
+    g = load_golden(name)
+    pts, dia = golden_meshes(g)
+    crit = make_crit(pkg, pts, dia, cuda_dev)
+    args = [T(g[k], cuda_dev) for k in ("pq", "pt", "gq", "gt", "obj")]
+    pp = crit.eval_poses(*args)
+    assert np.array_equal(pp["valid"], g["valid"])
+    assert np.array_equal(pp["hit"], g["hit"])            # bit-exact accept/reject
+    assert same_bits(pp["add"], g["add"])                 # bit-exact distances (bar: 1e-5 rel)
+    assert same_bits(pp["add_s"], g["adds"])
+    m = crit.eval_metrics(*args)
+    got = np.array([m["add_mean"], m["add_s_mean"], m["add_01d_acc"]], np.float64)
+    assert np.array_equal(got, g["agg"], equal_nan=True)
+    assert all(isinstance(v, np.float64) for v in m.values())
+
+
+def test_eval_empty_and_unknown_ids(pkg, cuda_dev, W):
+    crit = make_crit(pkg, {2: W.sphere_mesh(64, 0.1, 41)}, {}, cuda_dev)
+    pq, pt, gq, gt = (T(x, cuda_dev) for x in W.random_poses(4, 42))
+    m = crit.eval_metrics(pq, pt, gq, gt, torch.tensor([5, 5, 7, -1], device=cuda_dev))
+    assert m == {"add_mean": 0, "add_s_mean": 0, "add_01d_acc": 0}
+    assert all(isinstance(v, int) for v in m.values())
+    m = crit.eval_metrics(pq[:0], pt[:0], gq[:0], gt[:0], torch.zeros(0, dtype=torch.long, device=cuda_dev))
+    assert m == {"add_mean": 0, "add_s_mean": 0, "add_01d_acc": 0}
+    empty = pkg.ADDLoss(tempfile.mkdtemp(), cuda_dev)
+    assert empty.eval_metrics(pq, pt, gq, gt, torch.zeros(4, dtype=torch.long, device=cuda_dev))["add_mean"] == 0
+
+
+def test_host_tensors_are_accepted_and_mutation_rebuilds_table(pkg, cuda_dev, W, oracle):
+    pts = {0: W.sphere_mesh(300, 0.1, 7)}
+    crit = make_crit(pkg, pts, {0: 0.1}, cuda_dev)
+    pq, pt, gq, gt = W.random_poses(16, 8)
+    obj = np.zeros(16, np.int64)
+    a = crit.eval_poses(*(torch.from_numpy(x) for x in (pq, pt, gq, gt, obj)))     # CPU tensors in
+    ref = oracle.add_eval(oracle.MeshTable(pts, {0: 0.1}), pq, pt, gq, gt, obj)
+    assert same_bits(a["add"], ref[0]) and same_bits(a["add_s"], ref[1]) and np.array_equal(a["hit"], ref[2])
+    # mutate the public dicts (tests and SURVEY 0.5 do this): the device table must follow
+    pts2 = {0: W.sphere_mesh(180, 0.1, 9), 3: W.sphere_mesh(50, 0.2, 10)}
+    crit.points[0] = T(pts2[0], cuda_dev); crit.points[3] = T(pts2[3], cuda_dev); crit.diameters[3] = 0.05
+    obj[::2] = 3
+    b = crit.eval_poses(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
+    ref = oracle.add_eval(oracle.MeshTable(pts2, {0: 0.1, 3: 0.05}), pq, pt, gq, gt, obj)
+    assert same_bits(b["add"], ref[0]) and same_bits(b["add_s"], ref[1]) and np.array_equal(b["hit"], ref[2])
+
+
+def test_eval_large_mixed_batch_vs_oracle(pkg, cuda_dev, W, oracle):
+    """2,600 poses over the 13 LineMOD ids (500-point meshes, the reference's default size),
+    unsorted ids -> exercises the sorted-order path, mesh re-staging and the gt split."""
+    pts, dia = W.sweep_meshes(500)
+    r = np.random.RandomState(12)
+    B = 2600
+    pq, pt, gq, gt = W.random_poses(B, 13, rot_sigma=np.geomspace(0.005, 0.3, B))
+    obj = np.array(W.LINEMOD_IDS, np.int64)[r.randint(0, 13, B)]
+    obj[::97] = 2                                    # id without a mesh
+    crit = make_crit(pkg, pts, dia, cuda_dev)
+    got = crit.eval_poses(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
+    ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq, pt, gq, gt, obj, n_threads=oracle.max_threads())
+    assert np.array_equal(got["valid"], ref[3]) and np.array_equal(got["hit"], ref[2])
+    assert same_bits(got["add"], ref[0]) and same_bits(got["add_s"], ref[1])
+    assert 0 < got["hit"].sum() < got["valid"].sum()      # both decision outcomes exercised
+
+
+def test_add_only_kernel_vs_oracle(pkg, cuda_dev, W, oracle):
+    """Kernel (a): warp-per-pose ADD without the all-pairs part."""
+    pts, dia = W.sweep_meshes(500)
+    pts[1] = W.sphere_mesh(1000, dia[1], 77)
+    pts[4] = W.sphere_mesh(37, dia[4], 78)
+    B = 3000
+    pq, pt, gq, gt = W.random_poses(B, 14, rot_sigma=np.geomspace(0.005, 0.3, B))
+    obj = np.array(W.LINEMOD_IDS, np.int64)[np.random.RandomState(15).randint(0, 13, B)]
+    core = pkg.core
+    table = core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    d = [T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)]
+    add, adds, hit, valid, _ = table.evaluate(*d, want_adds=False)
+    assert adds is None
+    ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq, pt, gq, gt, obj, want_adds=False)
+    assert same_bits(add.cpu().numpy(), ref[0])
+    assert np.array_equal(hit.cpu().numpy(), ref[2]) and np.array_equal(valid.cpu().numpy(), ref[3])
+
+
+def test_host_entry_and_accumulators(pkg, cuda_dev, W):
+    """p6d_add_eval_host (host buffers, copies inside) == device entry; the per-object
+    atomics equal the per-pose outputs summed on the host."""
+    pts, dia = W.sweep_meshes(500)
+    B = 1500
+    pq, pt, gq, gt = W.random_poses(B, 21, rot_sigma=np.geomspace(0.01, 0.2, B))
+    obj = np.array(W.LINEMOD_IDS, np.int64)[np.arange(B) % 13]
+    table = pkg.core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    h = table.evaluate_host(pq, pt, gq, gt, obj)
+    add, adds, hit, valid, _ = table.evaluate(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
+    assert same_bits(h["add"], add.cpu().numpy()) and same_bits(h["adds"], adds.cpu().numpy())
+    assert np.array_equal(h["hit"], hit.cpu().numpy()) and np.array_equal(h["valid"], valid.cpu().numpy())
+    assert h["gpu_launches"] == 1
+    for o in W.LINEMOD_IDS:
+        sel = obj == o
+        assert h["obj_valid"][o] == sel.sum() and h["obj_hits"][o] == h["hit"][sel].sum()
+        assert np.isclose(h["obj_add_sum"][o], h["add"][sel].astype(np.float64).sum(), rtol=1e-12)
+        assert np.isclose(h["obj_adds_sum"][o], h["adds"][sel].astype(np.float64).sum(), rtol=1e-12)
+
+
+def test_config2_full_size_properties(pkg, cuda_dev, W, oracle):
+    """BASELINE config 2 at full size (65,536 poses, 2,048-point meshes): size-independent
+    properties plus a seeded subset against the oracle."""
+    pts, dia = W.config2_meshes(2048)
+    pq, pt, gq, gt, obj = W.config2(65536)
+    # plant exact-match poses: every distance must be exactly 0 and the pose accepted
+    pq[100:104] = gq[100:104]; pt[100:104] = gt[100:104]
+    table = pkg.core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    d = [T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)]
+    acc = [torch.zeros(table.n_slots, dtype=torch.int64, device=cuda_dev) for _ in range(2)] + \
+          [torch.zeros(table.n_slots, dtype=torch.float64, device=cuda_dev) for _ in range(2)]
+    order = torch.argsort(d[4], stable=True).to(torch.int32)
+    add, adds, hit, valid, _ = table.evaluate(*d, want_adds=True, order=order, acc=acc)
+    add, adds, hit, valid = (x.cpu().numpy() for x in (add, adds, hit, valid))
+    assert valid.all()
+    assert np.all(adds <= add)                       # min over j includes j == i, same rounding
+    assert not np.any(add[100:104]) and not np.any(adds[100:104]) and hit[100:104].all()
+    # decisions are consistent with the float64 threshold compare on the returned distances
+    thr = np.where(obj == 9, 0.1 * dia[9], 0.1 * dia[10])
+    assert np.array_equal(hit.astype(bool), adds.astype(np.float64) < thr)
+    # per-object accumulators (the quantities that get all-reduced) equal the per-pose sums
+    for o in (9, 10):
+        assert int(acc[0][o]) == int(hit[obj == o].sum()) and int(acc[1][o]) == int((obj == o).sum())
+    # processing order does not change any bit
+    perm = np.random.RandomState(3).permutation(65536)[:8192]
+    add2, adds2, hit2, _, _ = table.evaluate(*(x[torch.from_numpy(perm).to(cuda_dev)].contiguous() for x in d))
+    assert same_bits(add2.cpu().numpy(), add[perm]) and same_bits(adds2.cpu().numpy(), adds[perm])
+    assert np.array_equal(hit2.cpu().numpy(), hit[perm])
+    # seeded subset against the oracle (bit-exact)
+    sel = np.random.RandomState(4).choice(65536, 96, replace=False)
+    ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq[sel], pt[sel], gq[sel], gt[sel], obj[sel],
+                          n_threads=oracle.max_threads())
+    assert same_bits(add[sel], ref[0]) and same_bits(adds[sel], ref[1]) and np.array_equal(hit[sel], ref[2])
+
+
+def test_mesh_too_large_is_a_loud_error(pkg, cuda_dev, W):
+    n_max = pkg.core.C.c_int()
+    pkg.core.check(pkg.core.lib().p6d_adds_max_points(cuda_dev.index, pkg.core.C.byref(n_max)))
+    assert n_max.value >= 4096
+    crit = make_crit(pkg, {0: W.sphere_mesh(n_max.value + 64, 0.1, 1)}, {0: 0.1}, cuda_dev)
+    pq, pt, gq, gt = (T(x, cuda_dev) for x in W.random_poses(2, 2))
+    with pytest.raises(pkg.core.P6DError, match="at most"):
+        crit.eval_metrics(pq, pt, gq, gt, torch.zeros(2, dtype=torch.long, device=cuda_dev))
+    with pytest.raises(ValueError):
+        crit.eval_metrics(pq, pt[:1], gq, gt, torch.zeros(2, dtype=torch.long, device=cuda_dev))
+
+
+def test_add_forward_value(pkg, cuda_dev):
+    g = load_golden("add_forward")
+    pts, dia = golden_meshes(g)
+    crit = make_crit(pkg, pts, dia, cuda_dev)
+    args = [T(g[k], cuda_dev) for k in ("pq", "pt", "gq", "gt", "obj")]
+    loss = crit(*args)
+    assert loss.dim() == 0 and loss.device == cuda_dev
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert abs(crit.train_loss(*args).item() - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    none = crit(args[0][:2], args[1][:2], args[2][:2], args[3][:2], torch.tensor([6, 6], device=cuda_dev))
+    assert none.item() == 0.0 and none.requires_grad
+
+
+# ------------------------------------------------------------------ PoseLoss
+@pytest.mark.parametrize("mode", ["geodesic", "l1"])
+@pytest.mark.parametrize("tag,B", [("b32", 32), ("b5", 5)])
+def test_pose_loss_forward_backward_golden(pkg, cuda_dev, mode, tag, B):
+    g = load_golden("pose_loss_cfg3")
+    k = f"{mode}_{tag}_"
+    rot = T(g[k + "rot_in"], cuda_dev).requires_grad_(True)
+    trans = T(g[k + "trans_in"], cuda_dev).requires_grad_(True)
+    crit = pkg.PoseLoss(1.0, 10.0, mode)
+    loss = crit(rot, trans, T(g["gt_rot"][:B], cuda_dev), T(g["gt_trans"][:B], cuda_dev))
+    assert loss.dim() == 0
+    loss.backward()
+    assert abs(loss.item() - float(g[k + "loss"])) <= 1e-5 * abs(float(g[k + "loss"]))   # north-star tolerance
+    gq = g[k + "grad_rot"]
+    row_scale = np.maximum(np.abs(gq).max(1, keepdims=True), 1e-30)
+    assert np.all(np.abs(rot.grad.cpu().numpy() - gq) <= 1e-5 * row_scale)
+    assert same_bits(trans.grad.cpu().numpy(), g[k + "grad_trans"])
+    fn = crit._geodesic_distance if mode == "geodesic" else crit._quaternion_l1
+    rl = fn(T(g[k + "rot_in"], cuda_dev), T(g["gt_rot"][:B], cuda_dev)).item()
+    assert abs(rl - float(g[k + "rot"])) <= 1e-5 * abs(float(g[k + "rot"]))
+    if mode == "l1":   # no transcendental: the ordered mean makes it bit-exact
+        assert bits(np.float32(rl)) == bits(g[k + "rot"])
+
+
+def test_training_step_chain_rgb_geometric(pkg, cuda_dev):
+    """Config 3 as the training script runs it (reference train_rgb_geometric.py:104-108):
+    head output -> q/(|q|+1e-8) in autograd -> pinhole translation -> PoseLoss -> backward;
+    grads reach rot_raw and z_pred."""
+    g = load_golden("pose_loss_cfg3")
+    rot_raw = T(g["rot_raw"], cuda_dev).requires_grad_(True)
+    z = T(g["z_pred"], cuda_dev).requires_grad_(True)
+    rot = rot_raw / (torch.norm(rot_raw, dim=1, keepdim=True) + 1e-8)
+    trans = pkg.pinhole_translation(z, T(g["bbox_center"], cuda_dev), T(g["K"], cuda_dev))
+    loss = pkg.PoseLoss(1.0, 10.0, "geodesic")(rot, trans, T(g["gt_rot"], cuda_dev), T(g["gt_trans"], cuda_dev))
+    loss.backward()
+    assert abs(loss.item() - float(g["geodesic_b32_loss"])) <= 1e-5 * float(g["geodesic_b32_loss"])
+    assert np.allclose(z.grad.cpu().numpy(), g["geodesic_b32_grad_z"], rtol=1e-5, atol=1e-7)
+    ref = g["geodesic_b32_grad_rot_raw"]
+    got = rot_raw.grad.cpu().numpy()
+    finite = np.isfinite(ref).all(1)
+    scale = np.maximum(np.abs(ref[finite]).max(1, keepdims=True), 1e-30)
+    assert np.all(np.abs(got[finite] - ref[finite]) <= 2e-5 * scale)
+
+
+def test_pose_loss_weights_large_batch_and_no_grad(pkg, cuda_dev, W, oracle):
+    g = load_golden("pose_loss_cfg3")
+    a = T(g["rot_raw"], cuda_dev).requires_grad_(True)
+    b = T(g["pred_trans_direct"], cuda_dev).requires_grad_(True)
+    loss = pkg.PoseLoss(0.5, 2.0)(a, b, T(g["gt_rot"], cuda_dev), T(g["gt_trans"], cuda_dev), obj_ids=None)
+    (3.0 * loss).backward()                                   # upstream gradient != 1
+    assert abs(loss.item() - float(g["w_loss"])) <= 1e-5 * float(g["w_loss"])
+    ref = 3.0 * g["w_grad_rot"]
+    scale = np.maximum(np.abs(ref).max(1, keepdims=True), 1e-30)
+    assert np.all(np.abs(a.grad.cpu().numpy() - ref) <= 1e-5 * scale)
+    assert np.allclose(b.grad.cpu().numpy(), 3.0 * g["w_grad_trans"], rtol=1e-6)
+    # multi-CTA shape (B > 2048) against the oracle
+    B = 50000
+    pq, pt, gq, gt = W.random_poses(B, 33, rot_sigma=0.3, trans_sigma=0.05)
+    for mode in ("geodesic", "l1"):
+        x = T(pq, cuda_dev).requires_grad_(True); y = T(pt, cuda_dev).requires_grad_(True)
+        l = pkg.PoseLoss(1.0, 10.0, mode)(x, y, T(gq, cuda_dev), T(gt, cuda_dev))
+        l.backward()
+        o = oracle.pose_loss(pq, pt, gq, gt, 1.0, 10.0, mode)
+        assert abs(l.item() - float(o["loss"])) <= 1e-5 * float(o["loss"])
+        sc = np.maximum(np.abs(o["grad_q"]).max(1, keepdims=True), 1e-30)
+        assert np.all(np.abs(x.grad.cpu().numpy() - o["grad_q"]) <= 1e-5 * sc)
+        assert same_bits(y.grad.cpu().numpy(), o["grad_t"])
+        l2 = pkg.PoseLoss(1.0, 10.0, mode)(x.detach(), y.detach(), T(gq, cuda_dev), T(gt, cuda_dev))
+        assert not l2.requires_grad and l2.item() == l.item()      # workspace left clean, deterministic
+
+
+# ------------------------------------------------------------------ geometric translation
+def test_pinhole_forward_backward(pkg, cuda_dev):
+    g = load_golden("pinhole")
+    z = T(g["z"], cuda_dev).requires_grad_(True)
+    out = pkg.pinhole_translation(z, T(g["uv"], cuda_dev), T(g["K"], cuda_dev))
+    assert same_bits(out.detach().cpu().numpy(), g["out"])
+    out.backward(T(g["grad_out"], cuda_dev))
+    assert z.grad.shape == (32, 1)
+    assert np.allclose(z.grad.cpu().numpy(), g["grad_z"], rtol=1e-5, atol=1e-7)
+    out = pkg.pinhole_translation(T(g["z"], cuda_dev), T(g["uv"], cuda_dev), T(g["K_shared"], cuda_dev))
+    assert same_bits(out.cpu().numpy(), g["out_shared"])
+
+
+def test_depth_backproject(pkg, cuda_dev, W, oracle):
+    g = load_golden("depth_backproject")
+    depth, uv, K = W.config4(256, int(g["seed"]))
+    out = pkg.depth_backproject(T(depth, cuda_dev), T(uv, cuda_dev), T(K, cuda_dev))
+    assert same_bits(out.cpu().numpy(), g["out"])
+    out = pkg.depth_backproject(T(depth, cuda_dev), T(uv, cuda_dev), T(K[0], cuda_dev))
+    assert same_bits(out.cpu().numpy(), g["out_shared"])
+    # other crop size / clamp (explicit H, W instead of the hard-coded 224)
+    depth, uv, K = W.config4(64, 44, hw=(96, 128))
+    out = pkg.depth_backproject(T(depth, cuda_dev), T(uv, cuda_dev), T(K, cuda_dev), clamp_hi=95.0)
+    assert same_bits(out.cpu().numpy(), oracle.depth_backproject(depth, uv, K, clamp_hi=95.0))
+    with pytest.raises(pkg.core.P6DError):
+        pkg.depth_backproject(T(depth, cuda_dev), T(uv, cuda_dev), T(K, cuda_dev), clamp_hi=223.0)

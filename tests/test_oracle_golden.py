@@ -1,0 +1,115 @@
+"""CPU: the oracle (oracle/pose_oracle.c) against the golden vectors that
+oracle/gen_golden.py produced by running the reference itself.  This is the pin that
+lets the GPU tests trust the oracle."""
+import numpy as np
+import pytest
+
+from conftest import bits, golden_meshes, load_golden, same_bits
+
+EVAL_CASES = ["eval_cfg1", "eval_cfg1_mixed", "eval_cfg2_subset", "eval_ragged", "eval_default_diameter",
+              "eval_degenerate"]
+
+
+def test_quat_to_mat_bit_exact(oracle):
+    g = load_golden("quat_to_mat")
+    assert same_bits(oracle.quat_to_mat(g["q"]), g["R"])
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_eval_per_pose_bit_exact(oracle, name):
+    g = load_golden(name)
+    pts, dia = golden_meshes(g)
+    t = oracle.MeshTable(pts, dia)
+    add, adds, hit, valid = oracle.add_eval(t, g["pq"], g["pt"], g["gq"], g["gt"], g["obj"], n_threads=4)
+    assert np.array_equal(valid, g["valid"])
+    assert np.array_equal(hit, g["hit"])          # ADD-0.1d decisions: bit-exact
+    assert same_bits(add, g["add"])               # distances: bit-exact, stronger than the 1e-5 bar
+    assert same_bits(adds, g["adds"])
+
+
+@pytest.mark.parametrize("name", EVAL_CASES)
+def test_eval_aggregate_dict(oracle, name):
+    g = load_golden(name)
+    pts, dia = golden_meshes(g)
+    m = oracle.eval_metrics(oracle.MeshTable(pts, dia), g["pq"], g["pt"], g["gq"], g["gt"], g["obj"])
+    got = np.array([m["add_mean"], m["add_s_mean"], m["add_01d_acc"]], np.float64)
+    assert np.array_equal(got, g["agg"], equal_nan=True)
+
+
+def test_threads_do_not_change_results(oracle):
+    g = load_golden("eval_cfg1_mixed")
+    pts, dia = golden_meshes(g)
+    t = oracle.MeshTable(pts, dia)
+    a = oracle.add_eval(t, g["pq"], g["pt"], g["gq"], g["gt"], g["obj"], n_threads=1)
+    b = oracle.add_eval(t, g["pq"], g["pt"], g["gq"], g["gt"], g["obj"], n_threads=8)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+
+
+def test_aten_sum_matches_torch_cpu_sum(oracle):
+    """Live pin of the summation order: torch's own CPU sum/mean (library code, present on
+    every box) must equal the oracle bit for bit on x86 hosts with AVX2 or AVX-512."""
+    import torch
+    if torch.backends.cpu.get_cpu_capability() not in ("AVX2", "AVX512"):
+        pytest.skip("ATen vector width differs on this host")
+    r = np.random.RandomState(5)
+    for n in [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 100, 255, 500, 511, 512, 513, 1000,
+              2048, 4097, 8200, 20000]:
+        for _ in range(5):
+            x = (r.rand(n) * 0.02 + 1e-4).astype(np.float32)
+            t = torch.from_numpy(x)
+            assert bits(oracle.aten_sum(x)) == bits(np.float32(t.sum().item())), n
+            assert bits(oracle.aten_mean(x)) == bits(np.float32(t.mean().item())), n
+    assert oracle.aten_sum(np.zeros(0, np.float32)) == 0.0
+
+
+def test_add_forward_value(oracle):
+    g = load_golden("add_forward")
+    pts, dia = golden_meshes(g)
+    v = oracle.add_forward(oracle.MeshTable(pts, dia), g["pq"], g["pt"], g["gq"], g["gt"], g["obj"])
+    assert abs(float(v) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+
+
+@pytest.mark.parametrize("mode", ["geodesic", "l1"])
+@pytest.mark.parametrize("tag,B", [("b32", 32), ("b5", 5)])
+def test_pose_loss(oracle, mode, tag, B):
+    g = load_golden("pose_loss_cfg3")
+    k = f"{mode}_{tag}_"
+    r = oracle.pose_loss(g[k + "rot_in"], g[k + "trans_in"], g["gt_rot"][:B], g["gt_trans"][:B], 1.0, 10.0, mode)
+    rel = lambda a, b: abs(float(a) - float(b)) / abs(float(b))
+    assert rel(r["loss"], g[k + "loss"]) <= 1e-5       # tolerance stated by the north-star
+    assert rel(r["rot"], g[k + "rot"]) <= 1e-5
+    assert bits(r["trans"]) == bits(g[k + "trans"])     # no transcendental: bit-exact
+    gq = g[k + "grad_rot"]
+    row_scale = np.maximum(np.abs(gq).max(1, keepdims=True), 1e-30)
+    assert np.all(np.abs(r["grad_q"] - gq) <= 1e-5 * row_scale)
+    assert same_bits(r["grad_t"], g[k + "grad_trans"])
+
+
+def test_pose_loss_weights_and_unnormalised_inputs(oracle):
+    g = load_golden("pose_loss_cfg3")
+    r = oracle.pose_loss(g["rot_raw"], g["pred_trans_direct"], g["gt_rot"], g["gt_trans"], 0.5, 2.0, "geodesic")
+    assert abs(float(r["loss"]) - float(g["w_loss"])) <= 1e-5 * abs(float(g["w_loss"]))
+    gq = g["w_grad_rot"]
+    row_scale = np.maximum(np.abs(gq).max(1, keepdims=True), 1e-30)
+    assert np.all(np.abs(r["grad_q"] - gq) <= 1e-5 * row_scale)
+    assert np.abs(gq[3]).max() > 1e9          # zero quaternion row: 1/eps gradient, not NaN
+    assert not np.any(gq[0])                  # identical quaternions: zero gradient
+
+
+def test_pinhole(oracle):
+    g = load_golden("pinhole")
+    out, gz = oracle.pinhole(g["z"], g["uv"], g["K"], g["grad_out"])
+    assert same_bits(out, g["out"])
+    assert np.allclose(gz, g["grad_z"], rtol=1e-5, atol=1e-7)
+    out, _ = oracle.pinhole(g["z"], g["uv"], g["K_shared"])
+    assert same_bits(out, g["out_shared"])
+
+
+def test_depth_backproject(oracle, W):
+    g = load_golden("depth_backproject")
+    depth, uv, K = W.config4(256, int(g["seed"]))
+    assert np.array_equal(uv, g["uv"]) and np.array_equal(K, g["K"])
+    assert np.array_equal(depth[:2], g["depth2"], equal_nan=True)
+    assert same_bits(oracle.depth_backproject(depth, uv, K), g["out"])
+    assert same_bits(oracle.depth_backproject(depth, uv, K[0]), g["out_shared"])
