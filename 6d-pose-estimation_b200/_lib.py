@@ -30,6 +30,7 @@ EXPORTS = (
     "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_add_eval", "p6d_add_eval_host",
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
     "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject", "p6d_fp32_microbench",
+    "p6d_adds_timeline",
 )
 
 
@@ -83,6 +84,7 @@ def lib() -> C.CDLL:
     L.p6d_pinhole_bwd.argtypes = [vp, vp, vp, i32, i64, vp, i32, vp]
     L.p6d_depth_backproject.argtypes = [vp, i32, i32, vp, vp, i32, i64, f32, vp, i32, vp]
     L.p6d_fp32_microbench.argtypes = [i32, i32, i32, C.POINTER(f64), C.POINTER(f64)]
+    L.p6d_adds_timeline.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
     missing = [n for n in EXPORTS if not hasattr(L, n)]
     if missing:
         raise P6DError(f"{SO_PATH} is stale: missing symbols {missing}; rebuild it")
@@ -200,6 +202,20 @@ class MeshTable:
                                  C.byref(acc_struct) if acc_struct is not None else None,
                                  stream_ptr(dev)))
         return add, (adds if want_adds else None), hit, valid, out
+
+    def timeline(self, pq, pt, gq, gt, obj, order=None):
+        """Per-CTA {smid, start_ns, end_ns, poses} of one ADD-S launch (measurement helper)."""
+        B = obj.shape[0]
+        dev = self.device
+        out = torch.empty(10 * B + 16, dtype=torch.uint8, device=dev)
+        tl = np.zeros((4096, 4), np.uint64)
+        n = C.c_int(0)
+        torch.cuda.synchronize(dev)
+        check(lib().p6d_adds_timeline(self.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), ptr(order), B,
+                                      out[:4 * B].data_ptr(), out[4 * B:8 * B].data_ptr(),
+                                      out[8 * B:9 * B].data_ptr(), out[9 * B:10 * B].data_ptr(),
+                                      ptr(tl), 4096, C.byref(n)))
+        return tl[: n.value]
 
     # -- host-buffer evaluation (end-to-end path) -------------------------------------
     def evaluate_host(self, pq, pt, gq, gt, obj, want_adds=True, per_pose=True):

@@ -65,6 +65,8 @@ struct EvalArgs {
     uint8_t* valid;
     p6d_accumulators acc;
     int has_acc;
+    int* work_counter;              // dynamic pose scheduler of adds_cta_kernel (zeroed before launch)
+    unsigned long long* timeline;   // optional per-CTA [smid, t_start, t_end, poses] (measurement only)
 };
 
 __device__ __forceinline__ void accumulate(const EvalArgs& a, int64_t oid, bool is_hit, float add,
@@ -179,14 +181,28 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
     long long staged_oid = -1;
     uint32_t phase = 0;
 
-    for (int64_t it = blockIdx.x; it < a.B; it += gridDim.x) {
+    // Dynamic pose scheduler: CTAs co-resident on an SM do not progress at the same rate
+    // (the warp arbiter is not fair), so a static split leaves SMs half empty at the end.
+    // One atomic per pose, issued one pose ahead so its latency is never exposed.
+    __shared__ int s_next;
+    unsigned long long t_start = 0;
+    int done = 0;
+    if (a.timeline && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    if (tid == 0) s_next = atomicAdd(a.work_counter, 1);
+    __syncthreads();
+
+    for (;;) {
+        const int64_t it = s_next;
+        if (it >= a.B) break;
         const int64_t b = a.order ? a.order[it] : it;
         if (tid < 4) s_pose[tid] = __ldg(a.pq + 4 * b + tid);
         else if (tid < 8) s_pose[tid] = __ldg(a.gq + 4 * b + tid - 4);
         else if (tid < 11) s_pose[tid] = __ldg(a.pt + 3 * b + tid - 8);
         else if (tid < 14) s_pose[tid] = __ldg(a.gt + 3 * b + tid - 11);
         else if (tid == 32) s_oid = a.obj[b];
-        __syncthreads();  // also: previous iteration's readers of s_gt / s_dadd* are done
+        __syncthreads();  // also: previous iteration's readers of s_gt / s_dadd* / s_next are done
+        if (tid == 64) s_next = atomicAdd(a.work_counter, 1);  // consumed after >= 2 more barriers
+        ++done;
         const long long oid = s_oid;
         const bool known = oid >= 0 && oid < a.n_slots && a.slots[oid].count > 0;
         if (!known) {  // CTA-uniform
@@ -310,7 +326,17 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
                 accumulate(a, oid, is_hit, add, adds, true);
             }
         }
-        // the __syncthreads at the top of the next iteration protects s_gt / s_dadd*
+        // the __syncthreads at the top of the next iteration protects s_gt / s_dadd*;
+        // s_next (written after that barrier of THIS iteration) is visible since the
+        // barriers of phases B and C
+    }
+    if (a.timeline && tid == 0) {
+        unsigned long long t_end;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long* o = a.timeline + 4ull * blockIdx.x;
+        o[0] = smid; o[1] = t_start; o[2] = t_end; o[3] = (unsigned long long)done;
     }
 }
 
@@ -344,7 +370,7 @@ static int adds_max_points_for(int smem_limit) {
 }
 
 static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_adds, cudaStream_t st,
-                       int* launches) {
+                       int* launches, int* grid_out = nullptr) {
     if (args.B == 0) return P6D_OK;
     if (!want_adds) {
         int64_t blocks = (args.B + ADD_WARPS - 1) / ADD_WARPS;
@@ -372,9 +398,13 @@ static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_
     if (per_sm < 1) per_sm = 1;
     int64_t grid = static_cast<int64_t>(t->sm_count) * per_sm;
     if (grid > args.B) grid = args.B;
-    adds_cta_kernel<<<static_cast<unsigned>(grid), ADDS_T, smem, st>>>(args, t->max_count);
+    EvalArgs a2 = args;
+    a2.work_counter = t->d_counters + (t->counter_idx++ % P6D_NUM_COUNTERS);
+    P6D_CUDA(cudaMemsetAsync(a2.work_counter, 0, sizeof(int), st));
+    adds_cta_kernel<<<static_cast<unsigned>(grid), ADDS_T, smem, st>>>(a2, t->max_count);
     P6D_CUDA(cudaGetLastError());
     if (launches) ++*launches;
+    if (grid_out) *grid_out = static_cast<int>(grid);
     return P6D_OK;
 }
 
@@ -458,6 +488,7 @@ int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_
         rc = cuda_fail(e, what);
         if (t->d_soa) cudaFree(t->d_soa);
         if (t->d_slots) cudaFree(t->d_slots);
+        if (t->d_counters) cudaFree(t->d_counters);
         free(t->h_slots);
         delete t;
         return rc;
@@ -467,6 +498,7 @@ int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_
         return fail(e, "cudaDeviceGetAttribute");
     if ((e = cudaMalloc(&t->d_soa, soa.size() * sizeof(float))) != cudaSuccess) return fail(e, "cudaMalloc(soa)");
     if ((e = cudaMalloc(&t->d_slots, n_slots * sizeof(SlotInfo))) != cudaSuccess) return fail(e, "cudaMalloc(slots)");
+    if ((e = cudaMalloc(&t->d_counters, P6D_NUM_COUNTERS * sizeof(int))) != cudaSuccess) return fail(e, "cudaMalloc(counters)");
     if ((e = cudaMemcpy(t->d_soa, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e, "cudaMemcpy(soa)");
     if ((e = cudaMemcpy(t->d_slots, t->h_slots, n_slots * sizeof(SlotInfo), cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -483,6 +515,7 @@ int p6d_mesh_table_destroy(p6d_mesh_table* t) {
     if (t->h_pinned) cudaFreeHost(t->h_pinned);
     if (t->d_soa) cudaFree(t->d_soa);
     if (t->d_slots) cudaFree(t->d_slots);
+    if (t->d_counters) cudaFree(t->d_counters);
     free(t->h_slots);
     delete t;
     return P6D_OK;
@@ -576,6 +609,35 @@ int p6d_add_eval_host(p6d_mesh_table* t, const float* pq, const float* pt, const
     if (acc_add_sum) memcpy(acc_add_sum, h + 16 * ns, 8 * ns);
     if (acc_adds_sum) memcpy(acc_adds_sum, h + 24 * ns, 8 * ns);
     return P6D_OK;
+}
+
+int p6d_adds_timeline(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                      const float* gt, const int64_t* obj, const int32_t* order, int64_t B, float* add,
+                      float* adds, uint8_t* hit, uint8_t* valid, uint64_t* timeline_host, int max_ctas,
+                      int* n_ctas) {
+    if (!table || B <= 0 || !timeline_host || !n_ctas || !adds) { set_error("p6d_adds_timeline: bad arguments"); return P6D_EINVAL; }
+    DeviceGuard guard(table->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    unsigned long long* d_tl = nullptr;
+    P6D_CUDA(cudaMalloc(&d_tl, sizeof(unsigned long long) * 4 * 4096));
+    P6D_CUDA(cudaMemset(d_tl, 0, sizeof(unsigned long long) * 4 * 4096));
+    EvalArgs a{};
+    a.soa = table->d_soa; a.slots = table->d_slots; a.n_slots = table->n_slots;
+    a.pq = pq; a.pt = pt; a.gq = gq; a.gt = gt; a.obj = obj; a.order = order; a.B = B;
+    a.add = add; a.adds = adds; a.hit = hit; a.valid = valid; a.timeline = d_tl;
+    int grid = 0;
+    int rc = launch_eval(table, a, true, nullptr, nullptr, &grid);
+    if (rc == P6D_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize");
+    }
+    if (rc == P6D_OK) {
+        const int n = grid < max_ctas ? grid : max_ctas;
+        cudaMemcpy(timeline_host, d_tl, sizeof(unsigned long long) * 4 * n, cudaMemcpyDeviceToHost);
+        *n_ctas = n;
+    }
+    cudaFree(d_tl);
+    return rc;
 }
 
 int p6d_quat_to_mat(const float* q, int64_t B, float* R, int device, void* stream) {

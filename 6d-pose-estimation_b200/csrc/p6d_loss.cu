@@ -32,11 +32,12 @@ struct RowOut {
     float ad[3];   // |t_p - t_g|
 };
 
+// torch.norm over a [B,4] row is the unfused sequential sum of squares (oracle: p6o_norm4)
 __device__ __forceinline__ float norm4(const float* v) {
     float s = __fmul_rn(v[0], v[0]);
-    s = __fmaf_rn(v[1], v[1], s);
-    s = __fmaf_rn(v[2], v[2], s);
-    s = __fmaf_rn(v[3], v[3], s);
+    s = __fadd_rn(s, __fmul_rn(v[1], v[1]));
+    s = __fadd_rn(s, __fmul_rn(v[2], v[2]));
+    s = __fadd_rn(s, __fmul_rn(v[3], v[3]));
     return __fsqrt_rn(s);
 }
 

@@ -119,7 +119,7 @@ def config3(batch: int = 32, seed: int = 3, edge_rows: bool = True):
             "gt_rot": gq, "gt_trans": gt, "pred_trans_direct": pt}
 
 
-def config4(batch: int = 256, seed: int = 4, hw=(224, 224)):
+def config4(batch: int = 256, seed: int = 4, hw=(224, 224), clamp_hi: int = 223):
     """BASELINE config 4 at the reference API: depth crops [B,224,224] in metres with 10 %
     zeros and a few NaN / out-of-range pixels, crop-space centres partly outside the
     crop, per-row K_crop."""
@@ -141,7 +141,7 @@ def config4(batch: int = 256, seed: int = 4, hw=(224, 224)):
     K[:, 2, 2] = 1.0
     # force special depth values at the sampled pixel of a few rows
     def px(b):
-        u = int(np.clip(np.clip(uv[b, 0], 0, 223), 0, 223)); v = int(np.clip(np.clip(uv[b, 1], 0, 223), 0, 223))
+        u = int(np.clip(uv[b, 0], 0, clamp_hi)); v = int(np.clip(uv[b, 1], 0, clamp_hi))
         return v, u
     for b, val in ((4, np.nan), (5, 0.0), (6, 0.01), (7, 0.010001), (8, 0.05), (9, 2.5), (10, -1.0),
                    (11, np.inf), (12, 0.1), (13, 2.0)):

@@ -72,11 +72,18 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -85,7 +92,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -98,7 +105,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        inside = [l for (t, l) in self.lines if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.05)]
+        if not inside:
+            inside = [l for (_, l) in self.lines[-3:]]
+        for l in inside:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -215,16 +225,16 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)                # L2 flush between timed steps (outside the event pair)
@@ -233,6 +243,7 @@ def run_b200(args):
         ev[k][1].record()
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)

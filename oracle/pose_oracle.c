@@ -18,7 +18,8 @@
  * (torch 2.11.0, MKL 2024.2, AVX-512 host) and is restated here:
  *   - elementwise mul/add/sub: one rounding each, never contracted;
  *   - torch.mm([N,3] x [3,3]): k-sequential FMA chain  fma(p2,r2, fma(p1,r1, p0*r0));
- *   - torch.norm(v, dim=-1) over 3 (or 4) components: sqrt(fma(z,z, fma(y,y, x*x)));
+ *   - torch.norm(v, dim=-1) over 3 components: sqrt(fma(z,z, fma(y,y, x*x))); over the 4
+ *     components of a quaternion row: unfused sequential sum of squares;
  *   - Tensor.sum()/mean() over a contiguous float32 row: ATen's cascade_sum with
  *     256-bit vectors (8 lanes) x 4-way ILP x 4 cascade levels of 16 (see aten_sum);
  *   - the ADD-0.1d compare happens in float64 (Python floats).
@@ -324,11 +325,13 @@ P6O_API int p6o_add_eval(const float* mesh_xyz, const int32_t* offsets, const in
  * sign(0) = 0, minimum() splits ties in halves, where() routes no grad to its mask.
  * They are evaluated in float64 from the float32 forward intermediates and rounded once.
  * ---------------------------------------------------------------------------------- */
+/* torch.norm / F.normalize over a [B,4] row: measured to be the UNFUSED sequential sum
+ * ((x0^2 + x1^2) + x2^2) + x3^2 (unlike the 3-component rows, which take the FMA chain). */
 static inline float p6o_norm4(const float* v) {
     float s = v[0] * v[0];
-    s = fmaf(v[1], v[1], s);
-    s = fmaf(v[2], v[2], s);
-    s = fmaf(v[3], v[3], s);
+    s = s + v[1] * v[1];
+    s = s + v[2] * v[2];
+    s = s + v[3] * v[3];
     return sqrtf(s);
 }
 

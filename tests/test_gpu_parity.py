@@ -300,7 +300,7 @@ def test_depth_backproject(pkg, cuda_dev, W, oracle):
     out = pkg.depth_backproject(T(depth, cuda_dev), T(uv, cuda_dev), T(K[0], cuda_dev))
     assert same_bits(out.cpu().numpy(), g["out_shared"])
     # other crop size / clamp (explicit H, W instead of the hard-coded 224)
-    depth, uv, K = W.config4(64, 44, hw=(96, 128))
+    depth, uv, K = W.config4(64, 44, hw=(96, 128), clamp_hi=95)
     out = pkg.depth_backproject(T(depth, cuda_dev), T(uv, cuda_dev), T(K, cuda_dev), clamp_hi=95.0)
     assert same_bits(out.cpu().numpy(), oracle.depth_backproject(depth, uv, K, clamp_hi=95.0))
     with pytest.raises(pkg.core.P6DError):
