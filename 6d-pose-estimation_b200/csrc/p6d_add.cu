@@ -67,6 +67,7 @@ struct EvalArgs {
     int has_acc;
     int* work_counter;              // dynamic pose scheduler of adds_cta_kernel (zeroed before launch)
     unsigned long long* timeline;   // optional per-CTA [smid, t_start, t_end, poses] (measurement only)
+    int scan_reps;                  // measurement only: repeat the all-pairs scan (results unchanged)
 };
 
 __device__ __forceinline__ void accumulate(const EvalArgs& a, int64_t oid, bool is_hit, float add,
@@ -130,20 +131,19 @@ __global__ void __launch_bounds__(ADD_WARPS * 32) add_warp_kernel(EvalArgs a) {
 }
 
 // ------------------------------------------------------------------ kernel (b): ADD-S
-constexpr int ADDS_T = 256;  // threads per CTA
-constexpr int ADDS_K = 8;    // pred points per thread
 constexpr float SENTINEL = 1.0e18f;  // padded gt coordinate: (p - 1e18)^2 * 3 < FLT_MAX, never the min
+constexpr int ADDS_MAX_U = 2;        // largest quad-unroll of any variant (sizes the gt padding)
 
 // dynamic shared memory layout (floats), for a table whose largest mesh has Nmax points:
 //   mesh  [3 * Npmax]            staged by TMA; x | y | z, each Np long
-//   gt    [3 * Ngmax]            gt cloud as SoA, padded with SENTINEL to 4*S
+//   gt    [3 * Ngmax]            gt cloud as SoA, padded with SENTINEL to 4*S*U
 //   dadd  [Nmax], dadds [Nmax]   per-point distances for the ordered means
 //   mbar  8 bytes
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline int adds_ngmax(int nmax) { return round_up(nmax, 4) + 4 * 32 * ADDS_MAX_U; }
 static inline size_t adds_smem_bytes(int nmax) {
     const int np = round_up(nmax, 4);
-    const int ng = round_up(nmax, 4) + 4 * 32;
-    return sizeof(float) * (3 * (size_t)np + 3 * (size_t)ng + 2 * (size_t)round_up(nmax, 4)) + 16;
+    return sizeof(float) * (3 * (size_t)np + 3 * (size_t)adds_ngmax(nmax) + 2 * (size_t)np) + 16;
 }
 
 __device__ __forceinline__ void pair_tile(float px, float py, float pz, float2 gx, float2 gy, float2 gz,
@@ -158,17 +158,21 @@ __device__ __forceinline__ void pair_tile(float px, float py, float pz, float2 g
     m = min3_nan(m, s.x, s.y);
 }
 
-__global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nmax) {
+// T threads per CTA, K pred points per thread, MINB CTAs per SM, U gt quads per loop trip
+template <int T, int K, int MINB, int U>
+__global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int npmax = round_up(nmax, 4);
-    const int ngmax = npmax + 4 * 32;
+    const int ngmax = adds_ngmax(nmax);
     float* s_mesh = reinterpret_cast<float*>(smem_raw);
     float* s_gt = s_mesh + 3 * npmax;
     float* s_dadd = s_gt + 3 * ngmax;
     float* s_dadds = s_dadd + npmax;
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dadds + npmax);
     __shared__ float s_pose[14];
+    __shared__ float s_mean[2];
     __shared__ long long s_oid;
+    __shared__ int s_next;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -176,15 +180,13 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
         mbar_init(s_bar, 1);
         fence_mbar_init();
     }
-    __syncthreads();
 
     long long staged_oid = -1;
     uint32_t phase = 0;
 
     // Dynamic pose scheduler: CTAs co-resident on an SM do not progress at the same rate
-    // (the warp arbiter is not fair), so a static split leaves SMs half empty at the end.
-    // One atomic per pose, issued one pose ahead so its latency is never exposed.
-    __shared__ int s_next;
+    // (the warp arbiter is not fair: measured 8:1), so a static split leaves SMs half empty
+    // at the end.  One atomic per pose, issued one pose ahead so its latency is never exposed.
     unsigned long long t_start = 0;
     int done = 0;
     if (a.timeline && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -200,8 +202,8 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
         else if (tid < 11) s_pose[tid] = __ldg(a.pt + 3 * b + tid - 8);
         else if (tid < 14) s_pose[tid] = __ldg(a.gt + 3 * b + tid - 11);
         else if (tid == 32) s_oid = a.obj[b];
-        __syncthreads();  // also: previous iteration's readers of s_gt / s_dadd* / s_next are done
-        if (tid == 64) s_next = atomicAdd(a.work_counter, 1);  // consumed after >= 2 more barriers
+        __syncthreads();  // (A) also: previous pose's readers of s_gt / s_dadd* / s_mean / s_next are done
+        if (tid == 64) s_next = atomicAdd(a.work_counter, 1);  // read after barriers (B) and (C)
         ++done;
         const long long oid = s_oid;
         const bool known = oid >= 0 && oid < a.n_slots && a.slots[oid].count > 0;
@@ -232,44 +234,45 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
         const float* mx = s_mesh;
         const float* my = s_mesh + np;
         const float* mz = s_mesh + 2 * np;
-
-        float Rp[9], Rg[9], tp[3], tg[3];
-        quat_to_mat(s_pose, Rp);
-        quat_to_mat(s_pose + 4, Rg);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            tp[k] = s_pose[8 + k];
-            tg[k] = s_pose[11 + k];
-        }
         const int mode = s.xform_mode;
 
         // gt split: S lanes share one group of K pred points and scan 1/S of the gt quads
         int S = 1;
-        while (S < 32 && (ADDS_T / (2 * S)) * ADDS_K >= n) S *= 2;
-        const int groups = ADDS_T / S;
-        const int ng = round_up(n, 4 * S);
+        while (S < 32 && (T / (2 * S)) * K >= n) S *= 2;
+        const int groups = T / S;
+        const int ng = round_up(n, 4 * S * U);
         float* gx = s_gt;
         float* gy = s_gt + ng;
         float* gz = s_gt + 2 * ng;
 
         // phase B: gt cloud -> shared memory, ADD distances
-        for (int i = tid; i < ng; i += ADDS_T) {
-            if (i < n) {
-                const float x = mx[i], y = my[i], z = mz[i];
-                float px, py, pz, qx, qy, qz;
-                xform_point(mode, x, y, z, Rp, tp, px, py, pz);
-                xform_point(mode, x, y, z, Rg, tg, qx, qy, qz);
-                gx[i] = qx;
-                gy[i] = qy;
-                gz[i] = qz;
-                s_dadd[i] = __fsqrt_rn(sq3(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
-            } else {
-                gx[i] = SENTINEL;
-                gy[i] = SENTINEL;
-                gz[i] = SENTINEL;
+        {
+            float Rp[9], Rg[9], tp[3], tg[3];
+            quat_to_mat(s_pose, Rp);
+            quat_to_mat(s_pose + 4, Rg);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                tp[k] = s_pose[8 + k];
+                tg[k] = s_pose[11 + k];
+            }
+            for (int i = tid; i < ng; i += T) {
+                if (i < n) {
+                    const float x = mx[i], y = my[i], z = mz[i];
+                    float px, py, pz, qx, qy, qz;
+                    xform_point(mode, x, y, z, Rp, tp, px, py, pz);
+                    xform_point(mode, x, y, z, Rg, tg, qx, qy, qz);
+                    gx[i] = qx;
+                    gy[i] = qy;
+                    gz[i] = qz;
+                    s_dadd[i] = __fsqrt_rn(sq3(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
+                } else {
+                    gx[i] = SENTINEL;
+                    gy[i] = SENTINEL;
+                    gz[i] = SENTINEL;
+                }
             }
         }
-        __syncthreads();
+        __syncthreads();  // (B)
 
         // phase C: all-pairs scan
         const int g = tid / S, sp = tid % S;
@@ -277,46 +280,66 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
         const float4* gy4 = reinterpret_cast<const float4*>(gy);
         const float4* gz4 = reinterpret_cast<const float4*>(gz);
         const int nquads = ng >> 2;
-        for (int base = 0; base < n; base += groups * ADDS_K) {
-            float px[ADDS_K], py[ADDS_K], pz[ADDS_K], m[ADDS_K];
+        for (int rep = 0; rep < a.scan_reps; ++rep)
+        for (int base = 0; base < n; base += groups * K) {
+            float px[K], py[K], pz[K], m[K];
+            {
+                // recomputed here (not kept from phase B) so that no matrix is live in the scan
+                float Rp[9], tp[3];
+                quat_to_mat(s_pose, Rp);
 #pragma unroll
-            for (int k = 0; k < ADDS_K; ++k) {
-                const int i = base + g + k * groups;
-                const int ii = i < n ? i : 0;
-                xform_point(mode, mx[ii], my[ii], mz[ii], Rp, tp, px[k], py[k], pz[k]);
-                m[k] = __int_as_float(0x7f800000);  // +inf
+                for (int k = 0; k < 3; ++k) tp[k] = s_pose[8 + k];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int i = base + g + k * groups;
+                    const int ii = i < n ? i : 0;
+                    xform_point(mode, mx[ii], my[ii], mz[ii], Rp, tp, px[k], py[k], pz[k]);
+                    m[k] = __int_as_float(0x7f800000);  // +inf
+                }
             }
 #pragma unroll 1
-            for (int qd = sp; qd < nquads; qd += S) {
-                const float4 X = gx4[qd], Y = gy4[qd], Z = gz4[qd];
+            for (int qd = sp; qd < nquads; qd += S * U) {
+                float4 X[U], Y[U], Z[U];
 #pragma unroll
-                for (int k = 0; k < ADDS_K; ++k) {
-                    pair_tile(px[k], py[k], pz[k], make_float2(X.x, X.y), make_float2(Y.x, Y.y),
-                              make_float2(Z.x, Z.y), m[k]);
-                    pair_tile(px[k], py[k], pz[k], make_float2(X.z, X.w), make_float2(Y.z, Y.w),
-                              make_float2(Z.z, Z.w), m[k]);
+                for (int u = 0; u < U; ++u) {
+                    X[u] = gx4[qd + u * S];
+                    Y[u] = gy4[qd + u * S];
+                    Z[u] = gz4[qd + u * S];
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        pair_tile(px[k], py[k], pz[k], make_float2(X[u].x, X[u].y), make_float2(Y[u].x, Y[u].y),
+                                  make_float2(Z[u].x, Z[u].y), m[k]);
+                        pair_tile(px[k], py[k], pz[k], make_float2(X[u].z, X[u].w), make_float2(Y[u].z, Y[u].w),
+                                  make_float2(Z[u].z, Z[u].w), m[k]);
+                    }
                 }
             }
             for (int o = 1; o < S; o <<= 1) {
 #pragma unroll
-                for (int k = 0; k < ADDS_K; ++k) m[k] = min_nan(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
+                for (int k = 0; k < K; ++k) m[k] = min_nan(m[k], __shfl_xor_sync(0xffffffffu, m[k], o));
             }
             if (sp == 0) {
 #pragma unroll
-                for (int k = 0; k < ADDS_K; ++k) {
+                for (int k = 0; k < K; ++k) {
                     const int i = base + g + k * groups;
                     // sqrt is monotone and correctly rounded: sqrt(min s) == min sqrt(s)
                     if (i < n) s_dadds[i] = __fsqrt_rn(m[k]);
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();  // (C)
 
-        // phase D: ordered means (ATen summation order), decision, outputs
-        if (tid < 32) {
-            const float add = aten_mean_warp([&](int e) { return s_dadd[e]; }, n, lane);
-            const float adds = aten_mean_warp([&](int e) { return s_dadds[e]; }, n, lane);
-            if (lane == 0) {
+        // phase D: ordered means (ATen summation order) on warps 0 and 1, decision, outputs
+        if (tid < 64) {
+            const float* src = tid < 32 ? s_dadd : s_dadds;
+            const float mean = aten_mean_warp([&](int e) { return src[e]; }, n, lane);
+            if (lane == 0) s_mean[tid >> 5] = mean;
+            asm volatile("bar.sync 1, 64;" ::: "memory");
+            if (tid == 0) {
+                const float add = s_mean[0], adds = s_mean[1];
                 const float eff = s.symmetric ? adds : add;
                 const bool is_hit = static_cast<double>(eff) < s.threshold;
                 a.add[b] = add;
@@ -326,9 +349,7 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
                 accumulate(a, oid, is_hit, add, adds, true);
             }
         }
-        // the __syncthreads at the top of the next iteration protects s_gt / s_dadd*;
-        // s_next (written after that barrier of THIS iteration) is visible since the
-        // barriers of phases B and C
+        // barrier (A) of the next pose protects s_gt / s_dadd* / s_mean
     }
     if (a.timeline && tid == 0) {
         unsigned long long t_end;
@@ -338,6 +359,32 @@ __global__ void __launch_bounds__(ADDS_T, 2) adds_cta_kernel(EvalArgs a, int nma
         unsigned long long* o = a.timeline + 4ull * blockIdx.x;
         o[0] = smid; o[1] = t_start; o[2] = t_end; o[3] = (unsigned long long)done;
     }
+}
+
+// Kernel variants (P6D_ADDS_VARIANT selects one for experiments; 0 is the default)
+struct AddsVariant {
+    const char* name;
+    int threads;
+    const void* fn;
+};
+static const AddsVariant g_adds_variants[] = {
+    // default: 2 CTAs x 16 warps per SM, 62 registers; measured fastest on B200 (tools/variants.py)
+    {"T512_K4_B2_U2", 512, (const void*)adds_cta_kernel<512, 4, 2, 2>},
+    {"T256_K8_B2_U1", 256, (const void*)adds_cta_kernel<256, 8, 2, 1>},
+    {"T256_K8_B2_U2", 256, (const void*)adds_cta_kernel<256, 8, 2, 2>},
+    {"T512_K4_B2_U1", 512, (const void*)adds_cta_kernel<512, 4, 2, 1>},
+    {"T256_K4_B3_U2", 256, (const void*)adds_cta_kernel<256, 4, 3, 2>},
+};
+constexpr int N_ADDS_VARIANTS = sizeof(g_adds_variants) / sizeof(g_adds_variants[0]);
+
+static int adds_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("P6D_ADDS_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v >= N_ADDS_VARIANTS) v = 0;
+    }
+    return v;
 }
 
 // ------------------------------------------------------------------ quat -> R (API parity)
@@ -391,17 +438,24 @@ static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_
                   t->max_count, adds_max_points_for(limit));
         return P6D_ETOOBIG;
     }
-    P6D_CUDA(cudaFuncSetAttribute(adds_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+    const AddsVariant& var = g_adds_variants[adds_variant()];
+    P6D_CUDA(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_cta_kernel, ADDS_T, smem));
+    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, var.fn, var.threads, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = static_cast<int64_t>(t->sm_count) * per_sm;
     if (grid > args.B) grid = args.B;
     EvalArgs a2 = args;
+    {
+        const char* e = getenv("P6D_DEBUG_SCAN_REPS");
+        a2.scan_reps = e ? atoi(e) : 1;
+        if (a2.scan_reps < 1) a2.scan_reps = 1;
+    }
     a2.work_counter = t->d_counters + (t->counter_idx++ % P6D_NUM_COUNTERS);
     P6D_CUDA(cudaMemsetAsync(a2.work_counter, 0, sizeof(int), st));
-    adds_cta_kernel<<<static_cast<unsigned>(grid), ADDS_T, smem, st>>>(a2, t->max_count);
+    int nmax = t->max_count;
+    void* kargs[] = {&a2, &nmax};
+    P6D_CUDA(cudaLaunchKernel(var.fn, dim3(static_cast<unsigned>(grid)), dim3(var.threads), kargs, smem, st));
     P6D_CUDA(cudaGetLastError());
     if (launches) ++*launches;
     if (grid_out) *grid_out = static_cast<int>(grid);
