@@ -10,6 +10,9 @@ from .models.add_loss import ADDLoss, SYMMETRIC_OBJECT_IDS  # noqa: F401
 from .models.pose_loss import PoseLoss  # noqa: F401
 from .utils.camera import DEFAULT_K, depth_backproject, get_gt_and_K, pinhole_translation  # noqa: F401
 from . import workloads  # noqa: F401
+from . import sweep  # noqa: F401
+from .sweep import PoseEvaluator, evaluate_sweep, reference_batch_means, shard_range  # noqa: F401
 
 __all__ = ["ADDLoss", "PoseLoss", "SYMMETRIC_OBJECT_IDS", "DEFAULT_K", "get_gt_and_K",
-           "pinhole_translation", "depth_backproject", "core", "workloads"]
+           "pinhole_translation", "depth_backproject", "core", "workloads", "sweep", "PoseEvaluator",
+           "evaluate_sweep", "reference_batch_means", "shard_range"]
