@@ -5,7 +5,8 @@
 //   kind 0  FFMA  : 16 independent scalar FMA chains per thread
 //   kind 1  FFMA2 : 16 independent packed (f32x2) FMA chains per thread
 //   kind 2  MIX   : the ADD-S inner tile (3 FADD2 + FMUL2 + 2 FFMA2 + FMNMX3 per two pairs)
-//                   on register operands, no shared-memory traffic
+//                   on register operands that change every tile, no shared-memory traffic:
+//                   the issue-rate ceiling of the kernel's instruction mix
 // FLOP accounting: FMA = 2 FLOP per lane-op; MIX = 8 FLOP per pair (3 sub, 3 mul, 2 add),
 // the same convention as the kernel's algorithmic FLOPs.
 #include "p6d_common.cuh"
@@ -52,37 +53,39 @@ __global__ void __launch_bounds__(PK_T) peak_ffma2_kernel(float* out, int iters,
 }
 
 constexpr int MIX_K = 8;
-__global__ void __launch_bounds__(PK_T, 2) peak_mix_kernel(float* out, int iters, float g0) {
-    float px[MIX_K], py[MIX_K], pz[MIX_K], m[MIX_K];
+constexpr int MIX_INNER = 16;
+// ADD-S tile on register operands that change every tile (nothing is loop-invariant, so
+// the compiler cannot hoist any of the 6 packed ops): 8 "pred" points x 1 gt pair per
+// tile = 48 packed FMA-pipe instructions + 8 FMNMX3 + 1 scalar add.
+__global__ void __launch_bounds__(PK_T, 2) peak_mix_kernel(float* out, int iters, float a, float b) {
+    float2 v[16];
+    float m[MIX_K];
 #pragma unroll
-    for (int k = 0; k < MIX_K; ++k) {
-        px[k] = threadIdx.x * 1e-3f + k;
-        py[k] = k * 0.5f - threadIdx.x * 1e-3f;
-        pz[k] = 0.25f * k;
-        m[k] = 3.0e38f;
-    }
-    float2 gx = make_float2(g0, g0 + 1.0f), gy = make_float2(g0 * 0.5f, g0 - 1.0f), gz = make_float2(-g0, 2.0f * g0);
+    for (int i = 0; i < 16; ++i) v[i] = make_float2(threadIdx.x * 1e-3f + i, i - threadIdx.x * 1e-3f);
+#pragma unroll
+    for (int k = 0; k < MIX_K; ++k) m[k] = 3.0e38f;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < MIX_INNER; ++j) {
 #pragma unroll
             for (int k = 0; k < MIX_K; ++k) {
-                const float2 dx = sub2(make_float2(px[k], px[k]), gx);
-                const float2 dy = sub2(make_float2(py[k], py[k]), gy);
-                const float2 dz = sub2(make_float2(pz[k], pz[k]), gz);
+                const float px = a + k, py = b - k, pz = a * k;
+                const float2 dx = sub2(make_float2(px, px), v[(j + 0) & 15]);
+                const float2 dy = sub2(make_float2(py, py), v[(j + 1) & 15]);
+                const float2 dz = sub2(make_float2(pz, pz), v[(j + 2) & 15]);
                 float2 s = mul2(dx, dx);
                 s = fma2(dy, dy, s);
                 s = fma2(dz, dz, s);
                 m[k] = min3_nan(m[k], s.x, s.y);
             }
-            // change the "gt" operands so nothing is hoisted (2 extra scalar adds per 16 pairs)
-            gx.x += 1.0f;
-            gy.y -= 1.0f;
+            v[j & 15].x += 1.0f;  // keeps the "gt" operands changing
         }
     }
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < MIX_K; ++k) s += m[k];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i].x;
     if (s == 123.456f) out[0] = s;
 }
 
@@ -106,7 +109,7 @@ extern "C" int p6d_fp32_microbench(int kind, int device, int iters, double* tflo
     auto launch = [&](int n) {
         if (kind == 0) peak_ffma_kernel<<<grid, PK_T>>>(d_out, n, 1.0001f, 0.5f);
         else if (kind == 1) peak_ffma2_kernel<<<grid, PK_T>>>(d_out, n, 1.0001f, 0.5f);
-        else peak_mix_kernel<<<grid, PK_T>>>(d_out, n, 0.125f);
+        else peak_mix_kernel<<<grid, PK_T>>>(d_out, n, 1.0001f, 0.5f);
     };
     launch(iters / 4 + 1);  // warm-up
     P6D_CUDA(cudaDeviceSynchronize());
@@ -121,7 +124,7 @@ extern "C" int p6d_fp32_microbench(int kind, int device, int iters, double* tflo
     double flop;
     if (kind == 0) flop = threads * iters * (double)PK_INNER * PK_CHAINS * 2.0;
     else if (kind == 1) flop = threads * iters * (double)PK_INNER * PK_CHAINS * 4.0;
-    else flop = threads * iters * 8.0 * MIX_K * 2.0 /*pairs per tile*/ * 8.0 /*FLOP per pair*/;
+    else flop = threads * iters * (double)MIX_INNER * MIX_K * 2.0 /*pairs per tile*/ * 8.0 /*FLOP per pair*/;
     *ms = t;
     *tflops = flop / (t * 1e-3) / 1e12;
     cudaEventDestroy(e0);

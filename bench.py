@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--poses", type=int, default=POSES_PER_GPU, help="hypotheses per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=2048, help="poses timed on the CPU baseline")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="poses timed on the CPU baseline (0 = sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
     return ap.parse_args()
@@ -307,9 +308,14 @@ def run_b200(args):
                 "gpu_launches": timed_launches, "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
                 "add_01d_acc": 100.0 * hits / valid}
         if not args.no_cpu_baseline:
-            v, cores, dt = cpu_rate(W, args.cpu_sample)
+            n_cpu = args.cpu_sample
+            if n_cpu <= 0:
+                probe, _, _ = cpu_rate(W, 256)
+                n_cpu = int(min(B, max(256, probe * 12.0)))
+            v, cores, dt = cpu_rate(W, n_cpu)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_sample} poses of config 2, {dt:.1f} s"}
+                                    "sample": f"first {n_cpu} poses of the same config-2 workload, {dt:.1f} s, "
+                                              "oracle/pose_oracle.c (C restatement, bit-exact vs the reference)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
