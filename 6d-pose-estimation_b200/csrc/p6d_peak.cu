@@ -57,7 +57,7 @@ constexpr int MIX_INNER = 16;
 // ADD-S tile on register operands that change every tile (nothing is loop-invariant, so
 // the compiler cannot hoist any of the 6 packed ops): 8 "pred" points x 1 gt pair per
 // tile = 48 packed FMA-pipe instructions + 8 FMNMX3 + 1 scalar add.
-__global__ void __launch_bounds__(PK_T, 2) peak_mix_kernel(float* out, int iters, float a, float b) {
+__global__ void __launch_bounds__(PK_T, 4) peak_mix_kernel(float* out, int iters, float a, float b) {
     float2 v[16];
     float m[MIX_K];
 #pragma unroll
@@ -104,7 +104,7 @@ extern "C" int p6d_fp32_microbench(int kind, int device, int iters, double* tflo
     cudaEvent_t e0, e1;
     P6D_CUDA(cudaEventCreate(&e0));
     P6D_CUDA(cudaEventCreate(&e1));
-    const int per_sm = (kind == 2) ? 2 : 4;
+    const int per_sm = 4;
     const unsigned grid = (unsigned)(sms * per_sm);
     auto launch = [&](int n) {
         if (kind == 0) peak_ffma_kernel<<<grid, PK_T>>>(d_out, n, 1.0001f, 0.5f);
