@@ -30,7 +30,7 @@ EXPORTS = (
     "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_add_eval", "p6d_add_eval_host",
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
     "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject", "p6d_fp32_microbench",
-    "p6d_adds_timeline",
+    "p6d_adds_timeline", "p6d_add_backward",
 )
 
 
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
     L.p6d_pinhole_bwd.argtypes = [vp, vp, vp, i32, i64, vp, i32, vp]
     L.p6d_depth_backproject.argtypes = [vp, i32, i32, vp, vp, i32, i64, f32, vp, i32, vp]
     L.p6d_fp32_microbench.argtypes = [i32, i32, i32, C.POINTER(f64), C.POINTER(f64)]
+    L.p6d_add_backward.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, f32, vp, vp, vp]
     L.p6d_adds_timeline.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
     missing = [n for n in EXPORTS if not hasattr(L, n)]
     if missing:
@@ -243,6 +244,17 @@ class MeshTable:
                 "gpu_launches": launches.value,
                 "h2d_bytes": B * (16 + 16 + 12 + 12 + 8),
                 "d2h_bytes": (B * (4 + (4 if want_adds else 0) + 2) if per_pose else 0) + 32 * ns}
+
+
+def add_backward(saved, grad_out):
+    """Gradients of ADDLoss.forward w.r.t. (pred_r, pred_t) through p6d_add_backward."""
+    pq, pt, gq, gt, obj, _is_sym, _keep, count, table, dev = saved
+    go = grad_out.detach().to(dev, torch.float32).reshape(1).contiguous()
+    gq_out = torch.empty_like(pq)
+    gt_out = torch.empty_like(pt)
+    check(lib().p6d_add_backward(table.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), obj.shape[0], ptr(go),
+                                 1.0 / float(count), ptr(gq_out), ptr(gt_out), stream_ptr(dev)))
+    return gq_out, gt_out
 
 
 def device_info(device=0) -> dict:

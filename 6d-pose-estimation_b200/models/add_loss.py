@@ -238,8 +238,6 @@ class ADDLoss(nn.Module):
         core = _core()
         if saved is None:
             return None, None
-        if not hasattr(core.lib(), "p6d_add_backward"):
-            raise NotImplementedError("gradient of ADDLoss.forward needs p6d_add_backward (SURVEY.md N3)")
         return core.add_backward(saved, grad_out)
 
     # ------------------------------------------------------------------ quaternion -> matrix

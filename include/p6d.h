@@ -106,6 +106,16 @@ int p6d_add_eval_host(p6d_mesh_table* table, const float* pq, const float* pt, c
                       int64_t* acc_valid, double* acc_add_sum, double* acc_adds_sum,
                       int* gpu_launches);
 
+/* ---------------------------------------------------------------------------------------
+ * Gradient of ADDLoss.forward (models/add_loss.py:101-150) w.r.t. pred_r [B,4] and
+ * pred_t [B,3]:  loss = (1/count) * sum over valid samples of ADD (asymmetric ids) or
+ * ADD-S (symmetric ids).  grad_out: device pointer to the upstream scalar gradient;
+ * inv_count = 1 / number of valid samples.  Skipped samples get zero gradient.
+ * ------------------------------------------------------------------------------------- */
+int p6d_add_backward(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                     const float* gt, const int64_t* obj, int64_t B, const float* grad_out,
+                     float inv_count, float* grad_q, float* grad_t, void* stream);
+
 /* Measurement helper: runs the ADD-S kernel once (device buffers, legacy stream, synchronous)
  * and returns, per CTA, {smid, globaltimer start, globaltimer end, poses processed} so the
  * load balance of the persistent grid can be inspected.  timeline_host holds 4*max_ctas

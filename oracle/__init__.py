@@ -53,6 +53,8 @@ def lib() -> C.CDLL:
         L.p6o_add_eval.restype = C.c_int
         L.p6o_add_eval.argtypes = [fp, ip, ip, dp, bp, C.c_int, fp, fp, fp, fp, lp, C.c_int64,
                                    C.c_int, fp, fp, bp, bp, C.c_int]
+        L.p6o_add_backward.restype = C.c_int
+        L.p6o_add_backward.argtypes = [fp, ip, ip, bp, C.c_int, fp, fp, fp, fp, lp, C.c_int64, C.c_double, fp, fp]
         L.p6o_pose_loss.restype = C.c_int
         L.p6o_pose_loss.argtypes = [fp, fp, fp, fp, C.c_int64, C.c_float, C.c_float, C.c_int,
                                     fp, fp, fp, fp, fp, fp]
@@ -189,6 +191,22 @@ def add_forward(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids) -> np.flo
     if count == 0:
         return np.float32(0.0)
     return np.float32(total / np.float32(count))
+
+
+def add_backward(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids, grad_out=1.0):
+    """d ADDLoss.forward / d (pred_r, pred_t)  (autograd of models/add_loss.py:101-150)."""
+    pq, pt, gq, gt = (_f32(pred_q).reshape(-1, 4), _f32(pred_t).reshape(-1, 3),
+                      _f32(gt_q).reshape(-1, 4), _f32(gt_t).reshape(-1, 3))
+    obj = np.ascontiguousarray(obj_ids, dtype=np.int64).ravel()
+    gq_ = np.zeros_like(pq); gt_ = np.zeros_like(pt)
+    rc = lib().p6o_add_backward(_ptr(table.xyz, C.c_float), _ptr(table.offsets, C.c_int32),
+                                _ptr(table.counts, C.c_int32), _ptr(table.symmetric, C.c_uint8), table.n_slots,
+                                _ptr(pq, C.c_float), _ptr(pt, C.c_float), _ptr(gq, C.c_float), _ptr(gt, C.c_float),
+                                _ptr(obj, C.c_int64), obj.shape[0], float(grad_out), _ptr(gq_, C.c_float),
+                                _ptr(gt_, C.c_float))
+    if rc != 0:
+        raise MemoryError("oracle add_backward failed")
+    return gq_, gt_
 
 
 def pose_loss(pred_q, pred_t, gt_q, gt_t, rot_weight=1.0, trans_weight=1.0, mode="geodesic",

@@ -317,6 +317,73 @@ P6O_API int p6o_add_eval(const float* mesh_xyz, const int32_t* offsets, const in
 }
 
 /* ------------------------------------------------------------------------------------
+ * Gradient of ADDLoss.forward (models/add_loss.py:101-150) w.r.t. pred_r / pred_t, i.e.
+ * what autograd derives through matmul, norm, min and mean:
+ *   loss = (1/count) sum_b mean_i d_bi,  dL/dp_i = (1/(count*N)) (p_i - g*) / d  (0 if d == 0)
+ *   dL/dt = sum_i dL/dp_i,  dL/dR = sum_i dL/dp_i m_i^T,  dL/dq = J(_quat_to_mat)^T dL/dR.
+ * Forward quantities in float32 (same rounding as the loss), accumulation in float64.
+ * ---------------------------------------------------------------------------------- */
+P6O_API int p6o_add_backward(const float* mesh_xyz, const int32_t* offsets, const int32_t* counts,
+                             const uint8_t* symmetric, int n_slots, const float* pq, const float* pt,
+                             const float* gq, const float* gt, const int64_t* obj, int64_t B,
+                             double grad_out, float* grad_q, float* grad_t) {
+    int64_t count = 0, max_n = 1;
+    for (int64_t b = 0; b < B; ++b)
+        if (obj[b] >= 0 && obj[b] < n_slots && counts[obj[b]] > 0) ++count;
+    for (int s = 0; s < n_slots; ++s) if (counts[s] > max_n) max_n = counts[s];
+    float* g = (float*)malloc(sizeof(float) * 3 * (size_t)max_n);
+    if (!g) return -1;
+    for (int64_t b = 0; b < B; ++b) {
+        for (int k = 0; k < 4; ++k) grad_q[4 * b + k] = 0.0f;
+        for (int k = 0; k < 3; ++k) grad_t[3 * b + k] = 0.0f;
+        const int64_t oid = obj[b];
+        if (oid < 0 || oid >= n_slots || counts[oid] <= 0) continue;
+        const int64_t n = counts[oid];
+        const float* mesh = mesh_xyz + 3 * (int64_t)offsets[oid];
+        float Rp[9], Rg[9];
+        p6o_quat_to_mat(pq + 4 * b, Rp);
+        p6o_quat_to_mat(gq + 4 * b, Rg);
+        for (int64_t i = 0; i < n; ++i) p6o_xform_point(mesh + 3 * i, Rg, gt + 3 * b, n, g + 3 * i);
+        double T[3] = {0, 0, 0}, R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int64_t i = 0; i < n; ++i) {
+            float p[3];
+            p6o_xform_point(mesh + 3 * i, Rp, pt + 3 * b, n, p);
+            int64_t js = i;
+            if (symmetric[oid]) {
+                float best = INFINITY;
+                js = 0;
+                for (int64_t j = 0; j < n; ++j) {
+                    const float sv = p6o_sq3(p[0] - g[3 * j], p[1] - g[3 * j + 1], p[2] - g[3 * j + 2]);
+                    if (sv != sv) { js = j; break; }
+                    if (sv < best) { best = sv; js = j; }
+                }
+            }
+            const float d3[3] = {p[0] - g[3 * js], p[1] - g[3 * js + 1], p[2] - g[3 * js + 2]};
+            const float d = sqrtf(p6o_sq3(d3[0], d3[1], d3[2]));
+            if (d == 0.0f) continue;
+            for (int r = 0; r < 3; ++r) {
+                const double G = (double)(d3[r] / d);
+                T[r] += G;
+                for (int c = 0; c < 3; ++c) R[3 * r + c] += G * (double)mesh[3 * i + c];
+            }
+        }
+        const double scale = grad_out / (double)count / (double)n;
+        const double x = pq[4 * b], y = pq[4 * b + 1], z = pq[4 * b + 2], w = pq[4 * b + 3];
+        const double gx = 2*y*R[1] + 2*z*R[2] + 2*y*R[3] - 4*x*R[4] - 2*w*R[5] + 2*z*R[6] + 2*w*R[7] - 4*x*R[8];
+        const double gy = -4*y*R[0] + 2*x*R[1] + 2*w*R[2] + 2*x*R[3] + 2*z*R[5] - 2*w*R[6] + 2*z*R[7] - 4*y*R[8];
+        const double gz = -4*z*R[0] - 2*w*R[1] + 2*x*R[2] + 2*w*R[3] - 4*z*R[4] + 2*y*R[5] + 2*x*R[6] + 2*y*R[7];
+        const double gw = -2*z*R[1] + 2*y*R[2] + 2*z*R[3] - 2*x*R[5] - 2*y*R[6] + 2*x*R[7];
+        grad_q[4 * b + 0] = (float)(scale * gx);
+        grad_q[4 * b + 1] = (float)(scale * gy);
+        grad_q[4 * b + 2] = (float)(scale * gz);
+        grad_q[4 * b + 3] = (float)(scale * gw);
+        for (int k = 0; k < 3; ++k) grad_t[3 * b + k] = (float)(scale * T[k]);
+    }
+    free(g);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------
  * PoseLoss (models/pose_loss.py:19-61).  mode 0 = 'geodesic', 1 = quaternion L1.
  * Forward mirrors the float32 op order; per-row terms are returned so the caller can
  * check them independently of the mean.  Gradients (w.r.t. pred_rot, pred_trans, for

@@ -208,6 +208,34 @@ def test_add_forward_value(pkg, cuda_dev):
     assert none.item() == 0.0 and none.requires_grad
 
 
+def test_add_forward_backward(pkg, cuda_dev, W, oracle):
+    """N3: gradient of ADDLoss.forward vs the reference's autograd (golden) and vs the oracle
+    at a larger size (N = 2048 symmetric + asymmetric, where the reference needs ~GBs)."""
+    g = load_golden("add_forward")
+    pts, dia = golden_meshes(g)
+    crit = make_crit(pkg, pts, dia, cuda_dev)
+    pq = T(g["pq"], cuda_dev).requires_grad_(True); pt = T(g["pt"], cuda_dev).requires_grad_(True)
+    loss = crit(pq, pt, T(g["gq"], cuda_dev), T(g["gt"], cuda_dev), T(g["obj"], cuda_dev))
+    assert loss.requires_grad
+    (2.0 * loss).backward()
+    for got, ref in ((pq.grad, g["grad_q"]), (pt.grad, g["grad_t"])):
+        ref = 2.0 * ref
+        scale = np.maximum(np.abs(ref).max(1, keepdims=True), 1e-30)
+        assert np.all(np.abs(got.cpu().numpy() - ref) <= 1e-5 * scale)       # 1e-5 relative per row
+    pts2 = {3: W.sphere_mesh(2048, 0.17, 5), 10: W.box_mesh(2048, (0.04, 0.17, 0.04), 6)}
+    dia2 = {3: 0.17, 10: 0.176}
+    crit2 = make_crit(pkg, pts2, dia2, cuda_dev)
+    a, b, c, d = W.random_poses(6, 77, rot_sigma=0.1, trans_sigma=0.01)
+    obj = np.array([3, 10, 10, 3, 8, 10], np.int64)
+    x = T(a, cuda_dev).requires_grad_(True); y = T(b, cuda_dev).requires_grad_(True)
+    crit2(x, y, T(c, cuda_dev), T(d, cuda_dev), T(obj, cuda_dev)).backward()
+    rq, rt = oracle.add_backward(oracle.MeshTable(pts2, dia2), a, b, c, d, obj)
+    for got, ref in ((x.grad, rq), (y.grad, rt)):
+        scale = np.maximum(np.abs(ref).max(1, keepdims=True), 1e-30)
+        assert np.all(np.abs(got.cpu().numpy() - ref) <= 1e-5 * scale)
+    assert not torch.any(x.grad[4])
+
+
 # ------------------------------------------------------------------ PoseLoss
 @pytest.mark.parametrize("mode", ["geodesic", "l1"])
 @pytest.mark.parametrize("tag,B", [("b32", 32), ("b5", 5)])

@@ -70,6 +70,16 @@ def test_add_forward_value(oracle):
     assert abs(float(v) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
 
 
+def test_add_backward_matches_reference_autograd(oracle):
+    g = load_golden("add_forward")
+    pts, dia = golden_meshes(g)
+    gq, gt = oracle.add_backward(oracle.MeshTable(pts, dia), g["pq"], g["pt"], g["gq"], g["gt"], g["obj"])
+    for got, ref in ((gq, g["grad_q"]), (gt, g["grad_t"])):
+        scale = np.maximum(np.abs(ref).max(1, keepdims=True), 1e-30)
+        assert np.all(np.abs(got - ref) <= 1e-5 * scale)
+    assert not np.any(gq[g["obj"] == 6]) and np.any(gq[g["obj"] == 9])     # skipped id: zero grad
+
+
 @pytest.mark.parametrize("mode", ["geodesic", "l1"])
 @pytest.mark.parametrize("tag,B", [("b32", 32), ("b5", 5)])
 def test_pose_loss(oracle, mode, tag, B):
