@@ -83,6 +83,95 @@ __global__ void __launch_bounds__(CAM_T) depth_backproject_kernel(const float* _
     }
 }
 
+// ---------------------------------------------------------------------------------
+// N1: frame-level fusion of the reference's crop pipeline with (d2).
+// The reference (data/dataset_rgbd.py:104-179) pads the uint16 depth frame, cuts a square
+// crop of 1.2 x max(w,h), resizes it to 224^2 with cv2.resize(INTER_LINEAR) -- ~200 KB of
+// traffic per box -- and the network then reads ONE pixel of the result
+// (models/pose_net_rgbd_geometric.py:69-75).  Here one thread per box computes the crop
+// geometry (Python int / float64 semantics), the remapped centre and K_crop (NumPy
+// float32 semantics), evaluates cv2's generic bilinear formula at that single pixel from
+// 4 texels of the original frame (zero outside the frame = the constant border), and
+// back-projects.
+__device__ __forceinline__ void resize_axis(int d, long long cs, int img, int& s0, int& s1, float& w0, float& w1) {
+    const double scale = 1.0 / ((double)img / (double)cs);
+    const float v = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+    int s = (int)floorf(v);
+    float w = __fsub_rn(v, (float)s);
+    if (s < 0) { s = 0; w = 0.0f; }
+    if (s >= cs - 1) { s = (int)cs - 1; w = 0.0f; }
+    s0 = s;
+    s1 = s + 1 < cs ? s + 1 : (int)cs - 1;
+    w0 = __fsub_rn(1.0f, w);
+    w1 = w;
+}
+
+__global__ void __launch_bounds__(CAM_T) depth_crop_backproject_kernel(
+    const unsigned short* __restrict__ depth, int H, int W, const int* __restrict__ boxes, int64_t B,
+    const float* __restrict__ K, int img, float* __restrict__ xyz, float* __restrict__ center_out,
+    float* __restrict__ kcrop_out, unsigned short* __restrict__ zmm_out) {
+    const float fx = __ldg(K + 0), cx = __ldg(K + 2), fy = __ldg(K + 4), cy = __ldg(K + 5);
+    for (int64_t b = (int64_t)blockIdx.x * CAM_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * CAM_T) {
+        const int4 bb = *reinterpret_cast<const int4*>(boxes + 4 * b);
+        const int x = bb.x, y = bb.y, w = bb.z, h = bb.w;
+        // Python scalars: float64 and int() truncation toward zero
+        const double c_x = (double)x + (double)w / 2.0, c_y = (double)y + (double)h / 2.0;
+        const double size = (double)(w > h ? w : h) * 1.2;
+        long long x1 = (long long)__dsub_rn(c_x, size / 2.0), y1 = (long long)__dsub_rn(c_y, size / 2.0);
+        const long long cs = (long long)size;
+        if (cs < 1) {  // degenerate box: the reference would fail in cv2.resize; emit the fallback depth
+            xyz[3 * b] = 0.0f; xyz[3 * b + 1] = 0.0f; xyz[3 * b + 2] = 0.5f;
+            if (center_out) { center_out[2 * b] = 0.0f; center_out[2 * b + 1] = 0.0f; }
+            if (kcrop_out) for (int k = 0; k < 9; ++k) kcrop_out[9 * b + k] = 0.0f;
+            if (zmm_out) zmm_out[b] = 0;
+            continue;
+        }
+        const long long pad_l = x1 < 0 ? -x1 : 0, pad_t = y1 < 0 ? -y1 : 0;
+        x1 += pad_l;
+        y1 += pad_t;
+        // NumPy float32 arithmetic
+        const float scale32 = (float)((double)img / (double)cs);
+        const float hi = (float)(img - 1);
+        const float ccx = __fsub_rn(__fadd_rn((float)c_x, (float)pad_l), (float)x1);
+        const float ccy = __fsub_rn(__fadd_rn((float)c_y, (float)pad_t), (float)y1);
+        float u = __fmul_rn(ccx, scale32), v = __fmul_rn(ccy, scale32);
+        u = u < 0.0f ? 0.0f : (u > hi ? hi : u);   // np.clip(center_resized, 0, img-1)
+        v = v < 0.0f ? 0.0f : (v > hi ? hi : v);
+        const float fxc = __fmul_rn(fx, scale32), fyc = __fmul_rn(fy, scale32);
+        const float cxc = __fmul_rn(__fsub_rn(__fadd_rn(cx, (float)pad_l), (float)x1), scale32);
+        const float cyc = __fmul_rn(__fsub_rn(__fadd_rn(cy, (float)pad_t), (float)y1), scale32);
+        int ui = (int)u, vi = (int)v;              // .long(): truncation, then clamp
+        ui = ui < 0 ? 0 : (ui > img - 1 ? img - 1 : ui);
+        vi = vi < 0 ? 0 : (vi > img - 1 ? img - 1 : vi);
+        int sx0, sx1, sy0, sy1;
+        float a0, a1, b0, b1;
+        resize_axis(ui, cs, img, sx0, sx1, a0, a1);
+        resize_axis(vi, cs, img, sy0, sy1, b0, b1);
+        auto texel = [&](int yy, int xx) -> float {
+            const long long fy_ = y1 + yy - pad_t, fx_ = x1 + xx - pad_l;
+            if (fy_ < 0 || fy_ >= H || fx_ < 0 || fx_ >= W) return 0.0f;   // cv2.copyMakeBorder(..., value=0)
+            return (float)__ldg(depth + fy_ * W + fx_);
+        };
+        const float h0 = __fadd_rn(__fmul_rn(texel(sy0, sx0), a0), __fmul_rn(texel(sy0, sx1), a1));
+        const float h1 = __fadd_rn(__fmul_rn(texel(sy1, sx0), a0), __fmul_rn(texel(sy1, sx1), a1));
+        const float val = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+        int zi = __float2int_rn(val);              // saturate_cast<ushort>(cvRound)
+        zi = zi < 0 ? 0 : (zi > 65535 ? 65535 : zi);
+        float z = __fdiv_rn((float)zi, 1000.0f);
+        z = (z > 0.01f) ? z : 0.5f;
+        z = z < 0.1f ? 0.1f : (z > 2.0f ? 2.0f : z);
+        xyz[3 * b + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(u, cxc), z), fxc);
+        xyz[3 * b + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(v, cyc), z), fyc);
+        xyz[3 * b + 2] = z;
+        if (center_out) { center_out[2 * b] = u; center_out[2 * b + 1] = v; }
+        if (kcrop_out) {
+            float* k = kcrop_out + 9 * b;
+            k[0] = fxc; k[1] = 0.0f; k[2] = cxc; k[3] = 0.0f; k[4] = fyc; k[5] = cyc; k[6] = 0.0f; k[7] = 0.0f; k[8] = 1.0f;
+        }
+        if (zmm_out) zmm_out[b] = (unsigned short)zi;
+    }
+}
+
 static int grid_for(int64_t B, int device, unsigned* grid) {
     int sms = 0;
     P6D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -144,6 +233,25 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
     if (rc) return rc;
     depth_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(depth, H, W, uv, K, k_batched, B,
                                                                                     clamp_hi, out);
+    P6D_CUDA(cudaGetLastError());
+    return P6D_OK;
+}
+
+int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes, int64_t B,
+                               const float* K, int img_size, float* xyz, float* center, float* kcrop,
+                               uint16_t* z_mm, int device, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || img_size < 1 || (B > 0 && (!depth || !boxes || !K || !xyz))) {
+        set_error("p6d_depth_crop_backproject: bad arguments");
+        return P6D_EINVAL;
+    }
+    if (B == 0) return P6D_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    unsigned grid;
+    int rc = grid_for(B, device, &grid);
+    if (rc) return rc;
+    depth_crop_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
+        depth, H, W, boxes, B, K, img_size, xyz, center, kcrop, z_mm);
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;
 }

@@ -136,3 +136,38 @@ def depth_backproject(depth_raw, bbox_center, camera_matrix, clamp_hi=223.0):
                                                 float(clamp_hi), core.ptr(out), dev.index,
                                                 core.stream_ptr(dev)))
     return out
+
+
+@torch.no_grad()
+def depth_crop_backproject(depth_frame, boxes, camera_matrix, img_size=224, return_aux=False):
+    """XYZ for every (x, y, w, h) box of one uint16 depth frame [H,W] (millimetres) without
+    materialising any crop: the reference's pad / square-crop / cv2.resize / K remap
+    (data/dataset_rgbd.py:104-179) fused with its depth back-projection
+    (models/pose_net_rgbd_geometric.py:56-85).  `camera_matrix` is the frame's [3,3] K.
+    With return_aux also returns (centre [B,2], K_crop [B,3,3], z_mm [B] uint16)."""
+    core = _core()
+    if not isinstance(depth_frame, torch.Tensor):
+        depth_frame = torch.from_numpy(np.ascontiguousarray(depth_frame, dtype=np.uint16))
+    if not isinstance(boxes, torch.Tensor):
+        boxes = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.int32))
+    dev = core.require_cuda(depth_frame.device if depth_frame.is_cuda else boxes.device if boxes.is_cuda
+                            else camera_matrix.device)
+    if depth_frame.dim() != 2 or depth_frame.dtype not in (torch.uint16, torch.int16):
+        raise ValueError("depth_frame must be a [H,W] uint16 tensor (millimetres)")
+    d = depth_frame.to(dev).contiguous()
+    bx = boxes.to(dev, torch.int32).reshape(-1, 4).contiguous()
+    K = core.as_cuda_f32(camera_matrix, dev, ())
+    if K.numel() != 9:
+        raise ValueError("camera_matrix must be the frame's [3,3] intrinsics")
+    B = bx.shape[0]
+    H, W = d.shape
+    xyz = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    center = torch.empty(B, 2, dtype=torch.float32, device=dev) if return_aux else None
+    kcrop = torch.empty(B, 3, 3, dtype=torch.float32, device=dev) if return_aux else None
+    zmm = torch.empty(B, dtype=torch.int16, device=dev) if return_aux else None
+    core.check(core.lib().p6d_depth_crop_backproject(core.ptr(d), H, W, core.ptr(bx), B, core.ptr(K), int(img_size),
+                                                     core.ptr(xyz), core.ptr(center), core.ptr(kcrop), core.ptr(zmm),
+                                                     dev.index, core.stream_ptr(dev)))
+    if return_aux:
+        return xyz, center, kcrop, zmm.view(torch.uint16)
+    return xyz

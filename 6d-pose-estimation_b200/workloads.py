@@ -161,3 +161,30 @@ def sweep_meshes(n_points: int = 500):
             pts[oid] = sphere_mesh(n_points, d, 500 + oid)
         dia[oid] = d
     return pts, dia
+
+
+def config4_frame(seed: int = 40, n_boxes: int = 256, hw=(480, 640)):
+    """BASELINE config 4 at frame level: one uint16 depth frame in millimetres
+    (U(400,1500), 10 % zeros) and `n_boxes` integer (x, y, w, h) boxes, w,h in [40,200],
+    a third of them pushed against the image border so that the 1.2x square crop of the
+    reference (data/dataset_rgbd.py:122-145) needs zero padding."""
+    r = np.random.RandomState(seed)
+    H, W = hw
+    depth = r.randint(400, 1500, (H, W)).astype(np.uint16)
+    depth[r.rand(H, W) < 0.10] = 0
+    w = r.randint(40, 201, n_boxes)
+    h = r.randint(40, 201, n_boxes)
+    x = (r.rand(n_boxes) * (W - w)).astype(np.int64)
+    y = (r.rand(n_boxes) * (H - h)).astype(np.int64)
+    edge = np.arange(n_boxes) % 3 == 0
+    side = r.randint(0, 4, n_boxes)
+    x = np.where(edge & (side == 0), 0, x); x = np.where(edge & (side == 1), W - w, x)
+    y = np.where(edge & (side == 2), 0, y); y = np.where(edge & (side == 3), H - h, y)
+    boxes = np.stack([x, y, w, h], 1).astype(np.int32)
+    # a few hand-picked shapes: exact 2x / 1x resize factors, tiny and huge boxes
+    boxes[0] = (100, 100, 373, 200)      # size 447.6 -> crop 447
+    boxes[1] = (200, 150, 187, 100)      # size 224.4 -> crop 224 (identity resize)
+    boxes[2] = (10, 10, 20, 30)          # crop 36: up-sampling x6.2
+    boxes[3] = (0, 0, 640, 480)          # whole frame: crop 768, padded on all sides
+    boxes[4] = (300, 200, 374, 100)      # size 448.8 -> crop 448 (exact 2x)
+    return depth, boxes

@@ -163,6 +163,19 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
                           void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Frame-level fusion of the crop pipeline with the depth back-projection:
+ * LineMODDatasetRGBD.__getitem__ (data/dataset_rgbd.py:104-179: pad, square crop of
+ * 1.2 x max(w,h), cv2.resize to img_size, centre and K remapped into crop coordinates)
+ * followed by models/pose_net_rgbd_geometric.py:56-85, for B integer boxes (x,y,w,h) of ONE
+ * uint16 depth frame [H,W] in millimetres and the frame's intrinsics K [3,3].
+ *   xyz [B,3]; optional center [B,2] (crop-space bbox centre), kcrop [B,9], z_mm [B]
+ *   (the resized crop's uint16 value under the centre).  Bilinear = cv2's generic path.
+ * ------------------------------------------------------------------------------------- */
+int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes, int64_t B,
+                               const float* K, int img_size, float* xyz, float* center, float* kcrop,
+                               uint16_t* z_mm, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helper (no reference counterpart): FP32 issue-rate microbenchmarks that give
  * the roofline its measured denominator.  kind 0 = FFMA only, 1 = packed FFMA2 only,
  * 2 = the ADD-S instruction mix (3 FADD2 + FMUL2 + 2 FFMA2 + FMNMX3 per 2 pairs).

@@ -260,3 +260,70 @@ def depth_backproject(depth_raw, bbox_center, K, clamp_hi=223.0):
     lib().p6o_depth_backproject(_ptr(d, C.c_float), H, W, _ptr(uv, C.c_float), _ptr(Kf, C.c_float),
                                 kb, B, float(clamp_hi), _ptr(out, C.c_float))
     return out
+
+
+def crop_depth_backproject(depth_u16, boxes, K, img_size=224):
+    """N1 restatement (NumPy, per box): the crop geometry of LineMODDatasetRGBD.__getitem__
+    (data/dataset_rgbd.py:104-179, no augmentation), cv2.resize's generic INTER_LINEAR
+    path for uint16 evaluated at the single pixel the network reads, and the depth
+    back-projection of models/pose_net_rgbd_geometric.py:56-85.
+    Python-int / float64 arithmetic where the reference uses Python scalars, float32 where
+    it uses NumPy float32 (NumPy 2 promotion rules).  cv2 (OpenCV 4.x, resize.cpp):
+    fx = float((dx + 0.5) * scale - 0.5), scale = 1 / (dst / src) in double; weights
+    (1 - fx, fx) in float; horizontal then vertical pass as float mul, mul, add;
+    saturate_cast<ushort>(rint)."""
+    f = np.float32
+    depth = np.asarray(depth_u16)
+    H, Wd = depth.shape
+    K = np.asarray(K, np.float32)
+    B = len(boxes)
+    center = np.zeros((B, 2), f); Kc = np.zeros((B, 3, 3), f); z_mm = np.zeros(B, np.uint16); xyz = np.zeros((B, 3), f)
+
+    def texel(yy, xx, x1, y1, pad_l, pad_t):
+        # crop pixel (yy, xx) -> padded frame (y1 + yy, x1 + xx) -> frame (.. - pad); zero outside
+        fy, fx_ = y1 + yy - pad_t, x1 + xx - pad_l
+        if 0 <= fy < H and 0 <= fx_ < Wd:
+            return f(depth[fy, fx_])
+        return f(0)
+
+    def axis(d, cs):
+        scale = 1.0 / (float(img_size) / float(cs))
+        v = f((d + 0.5) * scale - 0.5)
+        s = int(np.floor(v))
+        w = f(v - f(s))
+        if s < 0:
+            s, w = 0, f(0)
+        if s >= cs - 1:
+            s, w = cs - 1, f(0)
+        return s, min(s + 1, cs - 1), f(f(1.0) - w), w
+
+    for b in range(B):
+        x, y, w, h = (int(v) for v in boxes[b])
+        cgt = np.array([x + w / 2, y + h / 2], dtype=f)
+        c_x, c_y = x + w / 2, y + h / 2
+        size = max(w, h) * 1.2
+        x1, y1 = int(c_x - size / 2), int(c_y - size / 2)
+        cs = int(size)
+        pad_l, pad_t = max(0, -x1), max(0, -y1)
+        x1 += pad_l; y1 += pad_t
+        scale32 = f(img_size / cs)
+        cc = np.array([f(f(cgt[0] + f(pad_l)) - f(x1)), f(f(cgt[1] + f(pad_t)) - f(y1))], f)
+        cr = np.clip((cc * scale32).astype(f), 0, img_size - 1).astype(f)
+        center[b] = cr
+        fx_, fy_, cx_, cy_ = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+        Kc[b] = np.array([[fx_ * scale32, 0, f(f(cx_ + f(pad_l)) - f(x1)) * scale32],
+                          [0, fy_ * scale32, f(f(cy_ + f(pad_t)) - f(y1)) * scale32], [0, 0, 1]], f)
+        u = min(max(cr[0], f(0)), f(img_size - 1)); v = min(max(cr[1], f(0)), f(img_size - 1))
+        ui, vi = min(max(int(u), 0), img_size - 1), min(max(int(v), 0), img_size - 1)
+        sx0, sx1, a0, a1 = axis(ui, cs)
+        sy0, sy1, b0, b1 = axis(vi, cs)
+        h0 = f(f(texel(sy0, sx0, x1, y1, pad_l, pad_t) * a0) + f(texel(sy0, sx1, x1, y1, pad_l, pad_t) * a1))
+        h1 = f(f(texel(sy1, sx0, x1, y1, pad_l, pad_t) * a0) + f(texel(sy1, sx1, x1, y1, pad_l, pad_t) * a1))
+        val = f(f(h0 * b0) + f(h1 * b1))
+        zi = int(np.clip(np.rint(val), 0, 65535))
+        z_mm[b] = zi
+        z = f(f(zi) / f(1000.0))
+        z = z if z > f(0.01) else f(0.5)
+        z = min(max(z, f(0.1)), f(2.0))
+        xyz[b] = (f(f(f(u - Kc[b, 0, 2]) * z) / Kc[b, 0, 0]), f(f(f(v - Kc[b, 1, 2]) * z) / Kc[b, 1, 1]), z)
+    return {"center": center, "Kcrop": Kc, "z_mm": z_mm, "xyz": xyz}

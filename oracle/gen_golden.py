@@ -262,9 +262,49 @@ def gen_loader():
     save("loader", **arrs)
 
 
+def gen_crop():
+    """N1: the reference's own crop pipeline (LineMODDatasetRGBD.__getitem__,
+    data/dataset_rgbd.py:85-206, cv2 pad/crop/resize on uint16) followed by its depth
+    back-projection, on one synthetic 480x640 frame with 256 boxes.  cv2's optimised
+    (IPP) bilinear differs from its generic C++ path by +-1 LSB in ~0.1 % of pixels, so
+    both are recorded."""
+    import cv2, yaml
+    from data.dataset_rgbd import LineMODDatasetRGBD
+    depth, boxes = W.config4_frame(40, 256)
+    root = tempfile.mkdtemp()
+    d = os.path.join(root, "01")
+    os.makedirs(os.path.join(d, "rgb")); os.makedirs(os.path.join(d, "depth"))
+    cv2.imwrite(os.path.join(d, "rgb", "0000.png"), np.zeros((480, 640, 3), np.uint8))
+    cv2.imwrite(os.path.join(d, "depth", "0000.png"), depth)
+    K = [float(v) for v in DEFAULT_K.reshape(-1)]
+    eye = [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0]
+    yaml.safe_dump({0: [{"obj_id": 1, "obj_bb": [int(v) for v in b], "cam_R_m2c": eye, "cam_t_m2c": [0.0, 0.0, 800.0]}
+                        for b in boxes]}, open(os.path.join(d, "gt.yml"), "w"))
+    yaml.safe_dump({0: {"cam_K": K, "depth_scale": 1.0}}, open(os.path.join(d, "info.yml"), "w"))
+    net = PoseNetRGBDGeometric.__new__(PoseNetRGBDGeometric)
+    out = {"seed": np.int64(40), "boxes": boxes, "K": DEFAULT_K.astype(np.float32)}
+    for tag, opt in (("generic", False), ("optimized", True)):
+        cv2.setUseOptimized(opt)
+        ds = LineMODDatasetRGBD(root, mode="train", augment_bbox=False)
+        assert len(ds) == len(boxes)
+        centers, Ks, raws, zs = [], [], [], []
+        for i in range(len(ds)):
+            _, _, depth_raw, _, _, _, c, Kc = ds[i]
+            centers.append(c.numpy()); Ks.append(Kc.numpy()); raws.append(depth_raw)
+        depth_raw = torch.stack(raws); c = T(np.stack(centers)); Kc = T(np.stack(Ks))
+        xyz = PoseNetRGBDGeometric._compute_pinhole_translation(net, depth_raw, c, Kc).numpy()
+        u = np.clip(np.clip(c.numpy()[:, 0], 0, 223).astype(np.int64), 0, 223)
+        v = np.clip(np.clip(c.numpy()[:, 1], 0, 223).astype(np.int64), 0, 223)
+        z_mm = np.rint(depth_raw.numpy()[np.arange(len(ds)), v, u] * 1000).astype(np.uint16)
+        out.update({f"{tag}_xyz": xyz, f"{tag}_z_mm": z_mm, f"{tag}_center": c.numpy(), f"{tag}_Kcrop": Kc.numpy()})
+    cv2.setUseOptimized(True)
+    out["cv2_version"] = np.array(cv2.__version__)
+    save("crop_backproject", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_quat(); gen_eval(); gen_forward(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader()
+    gen_quat(); gen_eval(); gen_forward(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/gen_golden.py from {REF}\n"
                 f"torch {torch.__version__} cpu_capability {torch.backends.cpu.get_cpu_capability()} "

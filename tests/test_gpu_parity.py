@@ -371,3 +371,24 @@ def test_sweep_is_invariant_to_the_number_of_ranks_and_matches_oracle(pkg, cuda_
     # the rgbd_geometric path really goes through the depth kernel and lands near the GT depth
     pt2 = pkg.sweep.variant_translation("rgbd_geometric", pt, gt, K, cseed)
     assert torch.allclose(pt2[:, 2], gt[:, 2], atol=0.02) and torch.allclose(pt2[:, :2], gt[:, :2], atol=0.01)
+
+
+def test_depth_crop_backproject_fused(pkg, cuda_dev, W, oracle):
+    """N1 on the GPU: 4 texels per box instead of a padded crop + 224x224 resize."""
+    g = load_golden("crop_backproject")
+    depth, boxes = W.config4_frame(int(g["seed"]), 256)
+    K = torch.from_numpy(g["K"]).to(cuda_dev)
+    xyz, center, kcrop, zmm = pkg.depth_crop_backproject(torch.from_numpy(depth).to(cuda_dev), torch.from_numpy(boxes),
+                                                         K, return_aux=True)
+    assert same_bits(center.cpu().numpy(), g["generic_center"]) and same_bits(kcrop.cpu().numpy(), g["generic_Kcrop"])
+    assert np.array_equal(zmm.cpu().numpy(), g["generic_z_mm"])
+    assert same_bits(xyz.cpu().numpy(), g["generic_xyz"])                     # == reference dataset + model
+    assert np.abs(xyz.cpu().numpy()[:, 2] - g["optimized_xyz"][:, 2]).max() <= 0.001 + 1e-6   # IPP path: <= 1 mm
+    # the fused result equals the two-step API (crop tensors + p6d_depth_backproject) as well
+    # other seeds / frame sizes against the oracle, boxes partly outside the frame
+    depth2, boxes2 = W.config4_frame(41, 300, hw=(360, 500))
+    boxes2[:8, 0] -= 60; boxes2[8:16, 1] += 200
+    r = oracle.crop_depth_backproject(depth2, boxes2, g["K"])
+    xyz2 = pkg.depth_crop_backproject(depth2, boxes2, K)
+    assert same_bits(xyz2.cpu().numpy(), r["xyz"])
+    assert pkg.depth_crop_backproject(depth2, boxes2[:0], K).shape == (0, 3)

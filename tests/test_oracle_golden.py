@@ -123,3 +123,17 @@ def test_depth_backproject(oracle, W):
     assert np.array_equal(depth[:2], g["depth2"], equal_nan=True)
     assert same_bits(oracle.depth_backproject(depth, uv, K), g["out"])
     assert same_bits(oracle.depth_backproject(depth, uv, K[0]), g["out_shared"])
+
+
+def test_crop_pipeline_restatement_matches_reference_dataset(oracle, W):
+    """N1: crop geometry + cv2 bilinear at the centre pixel + back-projection, against the
+    reference's LineMODDatasetRGBD + PoseNetRGBDGeometric run on a synthetic frame."""
+    g = load_golden("crop_backproject")
+    depth, boxes = W.config4_frame(int(g["seed"]), 256)
+    assert np.array_equal(boxes, g["boxes"])
+    r = oracle.crop_depth_backproject(depth, boxes, g["K"])
+    assert same_bits(r["center"], g["generic_center"]) and same_bits(r["Kcrop"], g["generic_Kcrop"])
+    assert np.array_equal(r["z_mm"], g["generic_z_mm"]) and same_bits(r["xyz"], g["generic_xyz"])
+    # cv2's optimised (IPP) bilinear may differ from its generic path by 1 LSB (1 mm)
+    assert np.abs(r["z_mm"].astype(int) - g["optimized_z_mm"].astype(int)).max() <= 1
+    assert np.mean(r["z_mm"] == g["optimized_z_mm"]) >= 0.99
