@@ -190,6 +190,8 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keeps stdout to the one JSON line of the contract
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = importlib.import_module("6d-pose-estimation_b200")
