@@ -64,6 +64,23 @@ def config_dict(args, extra=None):
     return c
 
 
+def profiled_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ADD-S kernel, from the newest
+    committed `ncu --set full` summary under profiles/ (same workload and launch shape as the bench)."""
+    import glob, re
+    best = None
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "adds_*_summary.txt"))):
+        txt = open(path).read()
+        r = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        w = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt)
+        if not r or not w:
+            continue
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        best = {"bytes": float(r.group(1)) * unit.get(r.group(2), 1.0) + float(w.group(1)) * unit.get(w.group(2), 1.0),
+                "source": os.path.relpath(path, REPO)}
+    return best
+
+
 # ------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons sampled during the timed region."""
@@ -286,8 +303,11 @@ def run_b200(args):
             pass
         sm_max = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
         nominal = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
+        tr = profiled_traffic() if B == POSES_PER_GPU else None
         roof = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s",
-                "frac": achieved / nominal, "traffic": None,
+                "frac": achieved / nominal, "traffic": tr["bytes"] if tr else None,
+                "traffic_source": tr["source"] if tr else None,
+                "algorithmic_bytes_per_launch": B * BYTES_PER_POSE,
                 "peak_source": f"nominal FFMA peak {info['sm_count']} SM x 128 lanes x 2 FLOP x {sm_max:.0f} MHz "
                                "(sm_max_mhz of MEASURED_PEAKS.json; that file has no FP32 entry -- the kernel "
                                "is neither HBM- nor tensor-bound, SURVEY 7.3.2)",

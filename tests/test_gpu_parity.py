@@ -110,6 +110,27 @@ def test_eval_large_mixed_batch_vs_oracle(pkg, cuda_dev, W, oracle):
     assert 0 < got["hit"].sum() < got["valid"].sum()      # both decision outcomes exercised
 
 
+def test_eval_ragged_large_meshes_vs_oracle(pkg, cuda_dev, W, oracle):
+    """Mesh sizes around every switch of the ADD-S kernel: gt-split factor S (powers of two
+    of threads*K), padded tails, one vs several passes over the pred points (N > 2048),
+    cascade levels of the ordered mean (N >= 512, 8192)."""
+    sizes = [128, 129, 255, 256, 257, 511, 512, 513, 1023, 1024, 1025, 2047, 2049, 3000, 4100, 5555]
+    pts, dia = {}, {}
+    for k, n in enumerate(sizes):
+        oid = k if k < 9 else k + 2                      # keep 9/10 free, then use them as symmetric ids
+        pts[oid] = W.sphere_mesh(n, 0.15, 700 + k); dia[oid] = 0.15
+    pts[9] = W.box_mesh(1500, (0.1, 0.12, 0.05), 790); dia[9] = 0.1646
+    pts[10] = W.box_mesh(2500, (0.04, 0.17, 0.04), 791); dia[10] = 0.1759
+    ids = np.array(sorted(pts), np.int64)
+    obj = np.repeat(ids, 2)
+    pq, pt, gq, gt = W.random_poses(len(obj), 71, rot_sigma=0.03, trans_sigma=0.004)
+    crit = make_crit(pkg, pts, dia, cuda_dev)
+    got = crit.eval_poses(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
+    ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq, pt, gq, gt, obj, n_threads=oracle.max_threads())
+    assert same_bits(got["add"], ref[0]) and same_bits(got["add_s"], ref[1])
+    assert np.array_equal(got["hit"], ref[2]) and got["valid"].all()
+
+
 def test_add_only_kernel_vs_oracle(pkg, cuda_dev, W, oracle):
     """Kernel (a): warp-per-pose ADD without the all-pairs part."""
     pts, dia = W.sweep_meshes(500)
