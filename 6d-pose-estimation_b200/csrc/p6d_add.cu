@@ -136,7 +136,8 @@ constexpr int ADDS_MAX_U = 2;        // largest quad-unroll of any variant (size
 
 // dynamic shared memory layout (floats), for a table whose largest mesh has Nmax points:
 //   mesh  [3 * Npmax]            staged by TMA; x | y | z, each Np long
-//   gt    [3 * Ngmax]            gt cloud as SoA, padded with SENTINEL to 4*S*U
+//   gt    [3 * Ngmax]            gt cloud as quads {x0..x3 | y0..y3 | z0..z3} (48 B per 4 points, one
+//                                pointer + immediate offsets in the scan), padded with SENTINEL to 4*S*U
 //   dadd  [Nmax], dadds [Nmax]   per-point distances for the ordered means
 //   mbar  8 bytes
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -156,6 +157,29 @@ __device__ __forceinline__ void pair_tile(float px, float py, float pz, float2 g
     s = fma2(dy, dy, s);
     s = fma2(dz, dz, s);
     m = min3_nan(m, s.x, s.y);
+}
+
+// U quads starting at p (quad stride `step` float4s) against K register-resident pred points
+template <int K, int U>
+__device__ __forceinline__ void scan_quads(const float4* __restrict__ p, int step, const float (&px)[K],
+                                           const float (&py)[K], const float (&pz)[K], float (&m)[K]) {
+    float4 X[U], Y[U], Z[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        X[u] = p[u * step + 0];
+        Y[u] = p[u * step + 1];
+        Z[u] = p[u * step + 2];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            pair_tile(px[k], py[k], pz[k], make_float2(X[u].x, X[u].y), make_float2(Y[u].x, Y[u].y),
+                      make_float2(Z[u].x, Z[u].y), m[k]);
+            pair_tile(px[k], py[k], pz[k], make_float2(X[u].z, X[u].w), make_float2(Y[u].z, Y[u].w),
+                      make_float2(Z[u].z, Z[u].w), m[k]);
+        }
+    }
 }
 
 // T threads per CTA, K pred points per thread, MINB CTAs per SM, U gt quads per loop trip
@@ -187,6 +211,8 @@ __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax)
     // Dynamic pose scheduler: CTAs co-resident on an SM do not progress at the same rate
     // (the warp arbiter is not fair: measured 8:1), so a static split leaves SMs half empty
     // at the end.  One atomic per pose, issued one pose ahead so its latency is never exposed.
+    // (Claiming several poses per atomic for small meshes was tried: it costs registers in
+    // the scan loop and gains < 4 % at N = 500.)
     unsigned long long t_start = 0;
     int done = 0;
     if (a.timeline && tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -241,9 +267,6 @@ __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax)
         while (S < 32 && (T / (2 * S)) * K >= n) S *= 2;
         const int groups = T / S;
         const int ng = round_up(n, 4 * S * U);
-        float* gx = s_gt;
-        float* gy = s_gt + ng;
-        float* gz = s_gt + 2 * ng;
 
         // phase B: gt cloud -> shared memory, ADD distances
         {
@@ -261,14 +284,16 @@ __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax)
                     float px, py, pz, qx, qy, qz;
                     xform_point(mode, x, y, z, Rp, tp, px, py, pz);
                     xform_point(mode, x, y, z, Rg, tg, qx, qy, qz);
-                    gx[i] = qx;
-                    gy[i] = qy;
-                    gz[i] = qz;
+                    float* gq = s_gt + (i >> 2) * 12 + (i & 3);   // conflict-free: 8 quads x 4 lanes per warp
+                    gq[0] = qx;
+                    gq[4] = qy;
+                    gq[8] = qz;
                     s_dadd[i] = __fsqrt_rn(sq3(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
                 } else {
-                    gx[i] = SENTINEL;
-                    gy[i] = SENTINEL;
-                    gz[i] = SENTINEL;
+                    float* gq = s_gt + (i >> 2) * 12 + (i & 3);
+                    gq[0] = SENTINEL;
+                    gq[4] = SENTINEL;
+                    gq[8] = SENTINEL;
                 }
             }
         }
@@ -276,9 +301,7 @@ __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax)
 
         // phase C: all-pairs scan
         const int g = tid / S, sp = tid % S;
-        const float4* gx4 = reinterpret_cast<const float4*>(gx);
-        const float4* gy4 = reinterpret_cast<const float4*>(gy);
-        const float4* gz4 = reinterpret_cast<const float4*>(gz);
+        const float4* gq4 = reinterpret_cast<const float4*>(s_gt);   // quad q at gq4[3q .. 3q+2]
         const int nquads = ng >> 2;
         for (int rep = 0; rep < a.scan_reps; ++rep)
         for (int base = 0; base < n; base += groups * K) {
@@ -297,25 +320,16 @@ __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax)
                     m[k] = __int_as_float(0x7f800000);  // +inf
                 }
             }
+            if (S == 1) {
+                // large meshes: unit stride, one pointer, immediate offsets
+                const float4* p = gq4;
+                const float4* const pend = gq4 + 3 * nquads;
 #pragma unroll 1
-            for (int qd = sp; qd < nquads; qd += S * U) {
-                float4 X[U], Y[U], Z[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    X[u] = gx4[qd + u * S];
-                    Y[u] = gy4[qd + u * S];
-                    Z[u] = gz4[qd + u * S];
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        pair_tile(px[k], py[k], pz[k], make_float2(X[u].x, X[u].y), make_float2(Y[u].x, Y[u].y),
-                                  make_float2(Z[u].x, Z[u].y), m[k]);
-                        pair_tile(px[k], py[k], pz[k], make_float2(X[u].z, X[u].w), make_float2(Y[u].z, Y[u].w),
-                                  make_float2(Z[u].z, Z[u].w), m[k]);
-                    }
-                }
+                for (; p < pend; p += 3 * U) scan_quads<K, U>(p, 3, px, py, pz, m);
+            } else {
+                const int step = 3 * S;
+#pragma unroll 1
+                for (int qd = sp; qd < nquads; qd += S * U) scan_quads<K, U>(gq4 + 3 * qd, step, px, py, pz, m);
             }
             for (int o = 1; o < S; o <<= 1) {
 #pragma unroll
@@ -368,23 +382,31 @@ struct AddsVariant {
     const void* fn;
 };
 static const AddsVariant g_adds_variants[] = {
-    // default: 2 CTAs x 16 warps per SM, 62 registers; measured fastest on B200 (tools/variants.py)
+    // 0: large meshes (1024 < N): 2 CTAs x 16 warps per SM, 63 registers; measured fastest on B200
     {"T512_K4_B2_U2", 512, (const void*)adds_cta_kernel<512, 4, 2, 2>},
     {"T256_K8_B2_U1", 256, (const void*)adds_cta_kernel<256, 8, 2, 1>},
     {"T256_K8_B2_U2", 256, (const void*)adds_cta_kernel<256, 8, 2, 2>},
     {"T512_K4_B2_U1", 512, (const void*)adds_cta_kernel<512, 4, 2, 1>},
     {"T256_K4_B3_U2", 256, (const void*)adds_cta_kernel<256, 4, 3, 2>},
+    // 5, 6: small meshes: one pose per 256 / 128 threads so that several poses per SM are in
+    // flight and hide each other's per-pose latencies (scheduler atomic, parameter loads, barriers)
+    {"T256_K4_B4_U2", 256, (const void*)adds_cta_kernel<256, 4, 4, 2>},
+    {"T128_K4_B8_U2", 128, (const void*)adds_cta_kernel<128, 4, 8, 2>},
 };
 constexpr int N_ADDS_VARIANTS = sizeof(g_adds_variants) / sizeof(g_adds_variants[0]);
 
-static int adds_variant() {
-    static int v = -1;
-    if (v < 0) {
+// Variant for a table whose largest mesh has nmax points; P6D_ADDS_VARIANT overrides (experiments).
+static int adds_variant(int nmax) {
+    static int forced = -2;
+    if (forced == -2) {
         const char* e = getenv("P6D_ADDS_VARIANT");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v >= N_ADDS_VARIANTS) v = 0;
+        forced = e ? atoi(e) : -1;
+        if (forced >= N_ADDS_VARIANTS) forced = -1;
     }
-    return v;
+    if (forced >= 0) return forced;
+    if (nmax <= 512) return 6;
+    if (nmax <= 1024) return 5;
+    return 0;
 }
 
 // ------------------------------------------------------------------ quat -> R (API parity)
@@ -438,7 +460,7 @@ static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_
                   t->max_count, adds_max_points_for(limit));
         return P6D_ETOOBIG;
     }
-    const AddsVariant& var = g_adds_variants[adds_variant()];
+    const AddsVariant& var = g_adds_variants[adds_variant(t->max_count)];
     P6D_CUDA(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
     P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, var.fn, var.threads, smem));

@@ -31,11 +31,16 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--one":
         one(int(sys.argv[2]), int(sys.argv[3]))
     else:
-        nv = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+        # first argument: number of variants (0..n-1) or a comma list, "auto" = library's own choice
+        arg = sys.argv[1] if len(sys.argv) > 1 else "8"
+        vs = [x for x in arg.split(",")] if ("," in arg or arg == "auto") else [str(i) for i in range(int(arg))]
         poses = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
         npts = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
-        for v in range(nv):
-            env = dict(os.environ, P6D_ADDS_VARIANT=str(v))
+        for v in vs:
+            env = dict(os.environ)
+            env.pop("P6D_ADDS_VARIANT", None)
+            if v != "auto":
+                env["P6D_ADDS_VARIANT"] = v
             r = subprocess.run([sys.executable, __file__, "--one", str(poses), str(npts)], env=env, capture_output=True, text=True)
             line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-300:]
             print(v, line, flush=True)
