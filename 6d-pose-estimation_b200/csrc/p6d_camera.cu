@@ -14,86 +14,40 @@ namespace p6d {
 
 constexpr int CAM_T = 256;
 
-// Row-wise kernels read [B,3] / [B,9] float rows.  Per-thread row accesses would be strided
-// (12 / 36 bytes); instead a CTA moves a tile of CAM_T rows as one flat, fully coalesced
-// float stream through shared memory (row strides 3 and 9 are odd -> conflict-free reads).
-template <int NF>
-__device__ __forceinline__ void tile_load(const float* __restrict__ g, int64_t row0, int rows, float* s) {
-    const float* src = g + row0 * NF;
-    const int n = rows * NF;
-#pragma unroll
-    for (int k = 0; k < NF; ++k) {
-        const int i = k * CAM_T + threadIdx.x;
-        if (i < n) s[i] = __ldg(src + i);
-    }
-}
-template <int NF>
-__device__ __forceinline__ void tile_store(float* __restrict__ g, int64_t row0, int rows, const float* s) {
-    float* dst = g + row0 * NF;
-    const int n = rows * NF;
-#pragma unroll
-    for (int k = 0; k < NF; ++k) {
-        const int i = k * CAM_T + threadIdx.x;
-        if (i < n) dst[i] = s[i];
-    }
-}
-
-struct KRow { float fx, fy, cx, cy; };
-__device__ __forceinline__ KRow k_row(const float* s_k, const float* __restrict__ K, int k_batched, int r) {
-    KRow o;
-    if (k_batched) { const float* k = s_k + 9 * r; o.fx = k[0]; o.cx = k[2]; o.fy = k[4]; o.cy = k[5]; }
-    else { o.fx = __ldg(K + 0); o.cx = __ldg(K + 2); o.fy = __ldg(K + 4); o.cy = __ldg(K + 5); }
-    return o;
+__device__ __forceinline__ void load_k(const float* __restrict__ K, int k_batched, int64_t b, float& fx,
+                                       float& fy, float& cx, float& cy) {
+    const float* k = K + (k_batched ? 9 * b : 0);
+    fx = __ldg(k + 0);
+    cx = __ldg(k + 2);
+    fy = __ldg(k + 4);
+    cy = __ldg(k + 5);
 }
 
 __global__ void __launch_bounds__(CAM_T) pinhole_fwd_kernel(const float* __restrict__ z, const float* __restrict__ uv,
                                                             const float* __restrict__ K, int k_batched, int64_t B,
                                                             float* __restrict__ out) {
-    __shared__ float s_k[9 * CAM_T];
-    __shared__ float s_o[3 * CAM_T];
-    const int64_t tiles = (B + CAM_T - 1) / CAM_T;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t row0 = t * CAM_T;
-        const int rows = B - row0 < CAM_T ? (int)(B - row0) : CAM_T;
-        __syncthreads();  // previous tile's readers are done
-        if (k_batched) tile_load<9>(K, row0, rows, s_k);
-        __syncthreads();
-        const int r = threadIdx.x;
-        if (r < rows) {
-            const KRow k = k_row(s_k, K, k_batched, r);
-            const float2 c = *reinterpret_cast<const float2*>(uv + 2 * (row0 + r));
-            const float zz = z[row0 + r];
-            s_o[3 * r + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(c.x, k.cx), zz), k.fx);
-            s_o[3 * r + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(c.y, k.cy), zz), k.fy);
-            s_o[3 * r + 2] = zz;
-        }
-        __syncthreads();
-        tile_store<3>(out, row0, rows, s_o);
+    for (int64_t b = (int64_t)blockIdx.x * CAM_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * CAM_T) {
+        float fx, fy, cx, cy;
+        load_k(K, k_batched, b, fx, fy, cx, cy);
+        const float2 c = *reinterpret_cast<const float2*>(uv + 2 * b);
+        const float zz = z[b];
+        out[3 * b + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(c.x, cx), zz), fx);
+        out[3 * b + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(c.y, cy), zz), fy);
+        out[3 * b + 2] = zz;
     }
 }
 
 __global__ void __launch_bounds__(CAM_T) pinhole_bwd_kernel(const float* __restrict__ go, const float* __restrict__ uv,
                                                             const float* __restrict__ K, int k_batched, int64_t B,
                                                             float* __restrict__ gz) {
-    __shared__ float s_k[9 * CAM_T];
-    __shared__ float s_g[3 * CAM_T];
-    const int64_t tiles = (B + CAM_T - 1) / CAM_T;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t row0 = t * CAM_T;
-        const int rows = B - row0 < CAM_T ? (int)(B - row0) : CAM_T;
-        __syncthreads();
-        if (k_batched) tile_load<9>(K, row0, rows, s_k);
-        tile_load<3>(go, row0, rows, s_g);
-        __syncthreads();
-        const int r = threadIdx.x;
-        if (r < rows) {
-            const KRow k = k_row(s_k, K, k_batched, r);
-            const float2 c = *reinterpret_cast<const float2*>(uv + 2 * (row0 + r));
-            // autograd order: d/dz[((u-cx)*z)/fx] = (g/fx)*(u-cx)
-            const float gx = __fmul_rn(__fdiv_rn(s_g[3 * r + 0], k.fx), __fsub_rn(c.x, k.cx));
-            const float gy = __fmul_rn(__fdiv_rn(s_g[3 * r + 1], k.fy), __fsub_rn(c.y, k.cy));
-            gz[row0 + r] = __fadd_rn(__fadd_rn(gx, gy), s_g[3 * r + 2]);
-        }
+    for (int64_t b = (int64_t)blockIdx.x * CAM_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * CAM_T) {
+        float fx, fy, cx, cy;
+        load_k(K, k_batched, b, fx, fy, cx, cy);
+        const float2 c = *reinterpret_cast<const float2*>(uv + 2 * b);
+        // autograd order: d/dz[((u-cx)*z)/fx] = (g/fx)*(u-cx)
+        const float gx = __fmul_rn(__fdiv_rn(go[3 * b + 0], fx), __fsub_rn(c.x, cx));
+        const float gy = __fmul_rn(__fdiv_rn(go[3 * b + 1], fy), __fsub_rn(c.y, cy));
+        gz[b] = __fadd_rn(__fadd_rn(gx, gy), go[3 * b + 2]);
     }
 }
 
@@ -108,37 +62,24 @@ __global__ void __launch_bounds__(CAM_T) depth_backproject_kernel(const float* _
                                                                   const float* __restrict__ K, int k_batched,
                                                                   int64_t B, float clamp_hi,
                                                                   float* __restrict__ out) {
-    __shared__ float s_k[9 * CAM_T];
-    __shared__ float s_o[3 * CAM_T];
     const long long hi = (long long)clamp_hi;
-    const int64_t tiles = (B + CAM_T - 1) / CAM_T;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t row0 = t * CAM_T;
-        const int rows = B - row0 < CAM_T ? (int)(B - row0) : CAM_T;
-        __syncthreads();
-        if (k_batched) tile_load<9>(K, row0, rows, s_k);
-        __syncthreads();
-        const int r = threadIdx.x;
-        if (r < rows) {
-            const int64_t b = row0 + r;
-            const KRow k = k_row(s_k, K, k_batched, r);
-            const float2 c = *reinterpret_cast<const float2*>(uv + 2 * b);
-            const float u = clamp_keep_nan(c.x, 0.0f, clamp_hi);
-            const float v = clamp_keep_nan(c.y, 0.0f, clamp_hi);
-            // .long(): truncation toward zero; NaN converts to INT64_MIN on the reference's x86 host
-            long long ui = (u != u) ? LLONG_MIN : (long long)u;
-            long long vi = (v != v) ? LLONG_MIN : (long long)v;
-            ui = ui < 0 ? 0 : (ui > hi ? hi : ui);
-            vi = vi < 0 ? 0 : (vi > hi ? hi : vi);
-            float zz = __ldg(depth + (b * H + vi) * W + ui);
-            zz = (zz > 0.01f) ? zz : 0.5f;  // false for NaN -> 0.5
-            zz = clamp_keep_nan(zz, 0.1f, 2.0f);
-            s_o[3 * r + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(u, k.cx), zz), k.fx);
-            s_o[3 * r + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(v, k.cy), zz), k.fy);
-            s_o[3 * r + 2] = zz;
-        }
-        __syncthreads();
-        tile_store<3>(out, row0, rows, s_o);
+    for (int64_t b = (int64_t)blockIdx.x * CAM_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * CAM_T) {
+        float fx, fy, cx, cy;
+        load_k(K, k_batched, b, fx, fy, cx, cy);
+        const float2 c = *reinterpret_cast<const float2*>(uv + 2 * b);
+        const float u = clamp_keep_nan(c.x, 0.0f, clamp_hi);
+        const float v = clamp_keep_nan(c.y, 0.0f, clamp_hi);
+        // .long(): truncation toward zero; NaN converts to INT64_MIN on the reference's x86 host
+        long long ui = (u != u) ? LLONG_MIN : (long long)u;
+        long long vi = (v != v) ? LLONG_MIN : (long long)v;
+        ui = ui < 0 ? 0 : (ui > hi ? hi : ui);
+        vi = vi < 0 ? 0 : (vi > hi ? hi : vi);
+        float zz = __ldg(depth + ((int64_t)b * H + vi) * W + ui);
+        zz = (zz > 0.01f) ? zz : 0.5f;  // false for NaN -> 0.5
+        zz = clamp_keep_nan(zz, 0.1f, 2.0f);
+        out[3 * b + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(u, cx), zz), fx);
+        out[3 * b + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(v, cy), zz), fy);
+        out[3 * b + 2] = zz;
     }
 }
 

@@ -41,11 +41,10 @@ __device__ __forceinline__ float norm4(const float* v) {
     return __fsqrt_rn(s);
 }
 
-// pt_row / gt_row / grad_t_row point at the 3 floats of row b (global or staged in shared memory)
-__device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* pt_row,
-                                           const float* __restrict__ gq, const float* gt_row,
+__device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* __restrict__ pt,
+                                           const float* __restrict__ gq, const float* __restrict__ gt,
                                            int64_t b, int64_t B, float wr, float wt, int mode,
-                                           float* __restrict__ grad_q, float* grad_t_row) {
+                                           float* __restrict__ grad_q, float* __restrict__ grad_t) {
     RowOut o;
     const float4 a4 = *reinterpret_cast<const float4*>(pq + 4 * b);
     const float4 c4 = *reinterpret_cast<const float4*>(gq + 4 * b);
@@ -127,9 +126,9 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
     const float tscale = (float)((double)wt / (3.0 * (double)B));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float df = __fsub_rn(pt_row[k], gt_row[k]);
+        const float df = __fsub_rn(pt[3 * b + k], gt[3 * b + k]);
         o.ad[k] = fabsf(df);
-        if (grad_t_row) grad_t_row[k] = df > 0.0f ? tscale : (df < 0.0f ? -tscale : 0.0f);
+        if (grad_t) grad_t[3 * b + k] = df > 0.0f ? tscale : (df < 0.0f ? -tscale : 0.0f);
     }
     return o;
 }
@@ -148,8 +147,7 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq
     __shared__ float s_rot[SMALL_B];
     __shared__ float s_ad[3 * SMALL_B];
     for (int b = threadIdx.x; b < B; b += LOSS_T) {
-        const RowOut o = loss_row(pq, pt + 3 * b, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q,
-                                  grad_t ? grad_t + 3 * b : nullptr);
+        const RowOut o = loss_row(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t);
         s_rot[b] = o.rot;
         s_ad[3 * b] = o.ad[0];
         s_ad[3 * b + 1] = o.ad[1];
@@ -169,36 +167,11 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq
                                                                  const float* gt, int64_t B, float wr, float wt,
                                                                  int mode, float* out, float* grad_q,
                                                                  float* grad_t, Workspace* ws) {
-    // [B,3] rows move as flat coalesced float streams through shared memory (tile of LOSS_T rows)
-    __shared__ float s_pt[3 * LOSS_T], s_gt[3 * LOSS_T], s_gr[3 * LOSS_T];
     double rs = 0.0, ts = 0.0;
-    const int64_t tiles = (B + LOSS_T - 1) / LOSS_T;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t row0 = t * LOSS_T;
-        const int rows = B - row0 < LOSS_T ? (int)(B - row0) : LOSS_T;
-        const int nf = 3 * rows;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int i = k * LOSS_T + threadIdx.x;
-            if (i < nf) { s_pt[i] = __ldg(pt + 3 * row0 + i); s_gt[i] = __ldg(gt + 3 * row0 + i); }
-        }
-        __syncthreads();
-        const int r = threadIdx.x;
-        if (r < rows) {
-            const RowOut o = loss_row(pq, s_pt + 3 * r, gq, s_gt + 3 * r, row0 + r, B, wr, wt, mode, grad_q,
-                                      grad_t ? s_gr + 3 * r : nullptr);
-            rs += (double)o.rot;
-            ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
-        }
-        if (grad_t) {
-            __syncthreads();
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int i = k * LOSS_T + threadIdx.x;
-                if (i < nf) grad_t[3 * row0 + i] = s_gr[i];
-            }
-        }
+    for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * LOSS_T) {
+        const RowOut o = loss_row(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t);
+        rs += (double)o.rot;
+        ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
