@@ -30,7 +30,7 @@ EXPORTS = (
     "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_add_eval", "p6d_add_eval_host",
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
     "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject", "p6d_fp32_microbench",
-    "p6d_adds_timeline", "p6d_add_backward", "p6d_depth_crop_backproject",
+    "p6d_adds_timeline", "p6d_add_backward", "p6d_depth_crop_backproject", "p6d_pose_loss_pinhole_fwd_bwd",
 )
 
 
@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     L.p6d_quat_to_mat.argtypes = [vp, i64, vp, i32, vp]
     L.p6d_pose_loss_workspace_bytes.restype = i64
     L.p6d_pose_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, i64, f32, f32, i32, vp, vp, vp, vp, i32, vp]
+    L.p6d_pose_loss_pinhole_fwd_bwd.argtypes = [vp, vp, vp, vp, i32, vp, vp, i64, f32, f32, i32, vp, vp, vp, vp, vp,
+                                                i32, vp]
     L.p6d_pinhole_fwd.argtypes = [vp, vp, vp, i32, i64, vp, i32, vp]
     L.p6d_pinhole_bwd.argtypes = [vp, vp, vp, i32, i64, vp, i32, vp]
     L.p6d_depth_backproject.argtypes = [vp, i32, i32, vp, vp, i32, i64, f32, vp, i32, vp]

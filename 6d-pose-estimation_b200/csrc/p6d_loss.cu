@@ -41,10 +41,11 @@ __device__ __forceinline__ float norm4(const float* v) {
     return __fsqrt_rn(s);
 }
 
-__device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* __restrict__ pt,
-                                           const float* __restrict__ gq, const float* __restrict__ gt,
+// pt_row / gt_row / grad_t_row point at the 3 floats of row b
+__device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* pt_row,
+                                           const float* __restrict__ gq, const float* gt_row,
                                            int64_t b, int64_t B, float wr, float wt, int mode,
-                                           float* __restrict__ grad_q, float* __restrict__ grad_t) {
+                                           float* __restrict__ grad_q, float* grad_t_row) {
     RowOut o;
     const float4 a4 = *reinterpret_cast<const float4*>(pq + 4 * b);
     const float4 c4 = *reinterpret_cast<const float4*>(gq + 4 * b);
@@ -126,9 +127,49 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
     const float tscale = (float)((double)wt / (3.0 * (double)B));
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float df = __fsub_rn(pt[3 * b + k], gt[3 * b + k]);
+        const float df = __fsub_rn(pt_row[k], gt_row[k]);
         o.ad[k] = fabsf(df);
-        if (grad_t) grad_t[3 * b + k] = df > 0.0f ? tscale : (df < 0.0f ? -tscale : 0.0f);
+        if (grad_t_row) grad_t_row[k] = df > 0.0f ? tscale : (df < 0.0f ? -tscale : 0.0f);
+    }
+    return o;
+}
+
+// Optional fused geometric translation (kernel d1 inside kernel c): pred_trans is not read
+// from memory but computed from (z, bbox centre, K) exactly like p6d_pinhole_fwd, and the
+// gradient w.r.t. z is produced exactly like p6d_pinhole_bwd applied to grad_trans.
+struct Geo {
+    const float* z;      // [B]   (nullptr = plain PoseLoss on pred_trans)
+    const float* uv;     // [B,2]
+    const float* K;      // [3,3] or [B,3,3]
+    int k_batched;
+    float* grad_z;       // [B] nullable
+    float* trans_out;    // [B,3] nullable: the translation the reference's model would return
+};
+
+__device__ __forceinline__ RowOut loss_row_any(const float* __restrict__ pq, const float* __restrict__ pt,
+                                               const float* __restrict__ gq, const float* __restrict__ gt,
+                                               int64_t b, int64_t B, float wr, float wt, int mode,
+                                               float* __restrict__ grad_q, float* __restrict__ grad_t,
+                                               const Geo& geo) {
+    if (!geo.z) return loss_row(pq, pt + 3 * b, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q,
+                                grad_t ? grad_t + 3 * b : nullptr);
+    const float* k = geo.K + (geo.k_batched ? 9 * b : 0);
+    const float fx = __ldg(k + 0), cx = __ldg(k + 2), fy = __ldg(k + 4), cy = __ldg(k + 5);
+    const float2 c = *reinterpret_cast<const float2*>(geo.uv + 2 * b);
+    const float zz = geo.z[b];
+    const float du = __fsub_rn(c.x, cx), dv = __fsub_rn(c.y, cy);
+    float t3[3] = {__fdiv_rn(__fmul_rn(du, zz), fx), __fdiv_rn(__fmul_rn(dv, zz), fy), zz};
+    float g3[3] = {0.0f, 0.0f, 0.0f};
+    const RowOut o = loss_row(pq, t3, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q, geo.grad_z ? g3 : nullptr);
+    if (geo.trans_out) {
+        geo.trans_out[3 * b + 0] = t3[0];
+        geo.trans_out[3 * b + 1] = t3[1];
+        geo.trans_out[3 * b + 2] = t3[2];
+    }
+    if (geo.grad_z) {
+        const float gx = __fmul_rn(__fdiv_rn(g3[0], fx), du);
+        const float gy = __fmul_rn(__fdiv_rn(g3[1], fy), dv);
+        geo.grad_z[b] = __fadd_rn(__fadd_rn(gx, gy), g3[2]);
     }
     return o;
 }
@@ -143,11 +184,11 @@ __device__ __forceinline__ void finish(float rot, float tr, float wr, float wt, 
 __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq, const float* pt, const float* gq,
                                                                  const float* gt, int B, float wr, float wt,
                                                                  int mode, float* out, float* grad_q,
-                                                                 float* grad_t) {
+                                                                 float* grad_t, Geo geo) {
     __shared__ float s_rot[SMALL_B];
     __shared__ float s_ad[3 * SMALL_B];
     for (int b = threadIdx.x; b < B; b += LOSS_T) {
-        const RowOut o = loss_row(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t);
+        const RowOut o = loss_row_any(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         s_rot[b] = o.rot;
         s_ad[3 * b] = o.ad[0];
         s_ad[3 * b + 1] = o.ad[1];
@@ -166,10 +207,10 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq
 __global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq, const float* pt, const float* gq,
                                                                  const float* gt, int64_t B, float wr, float wt,
                                                                  int mode, float* out, float* grad_q,
-                                                                 float* grad_t, Workspace* ws) {
+                                                                 float* grad_t, Workspace* ws, Geo geo) {
     double rs = 0.0, ts = 0.0;
     for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * LOSS_T) {
-        const RowOut o = loss_row(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t);
+        const RowOut o = loss_row_any(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         rs += (double)o.rot;
         ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
     }
@@ -211,21 +252,17 @@ extern "C" {
 
 int64_t p6d_pose_loss_workspace_bytes(void) { return (int64_t)sizeof(Workspace); }
 
-int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, const float* gt, int64_t B,
-                          float rot_weight, float trans_weight, int mode, float* out, float* grad_q,
-                          float* grad_t, void* workspace, int device, void* stream) {
-    if (B <= 0 || !pq || !pt || !gq || !gt || !out || (mode != 0 && mode != 1)) {
-        set_error("p6d_pose_loss_fwd_bwd: bad arguments (B=%lld, mode=%d)", (long long)B, mode);
-        return P6D_EINVAL;
-    }
+static int launch_pose_loss(const float* pq, const float* pt, const float* gq, const float* gt, int64_t B,
+                            float rot_weight, float trans_weight, int mode, float* out, float* grad_q,
+                            float* grad_t, void* workspace, int device, void* stream, const Geo& geo) {
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (B <= SMALL_B) {
         pose_loss_small_kernel<<<1, LOSS_T, 0, st>>>(pq, pt, gq, gt, (int)B, rot_weight, trans_weight, mode, out,
-                                                     grad_q, grad_t);
+                                                     grad_q, grad_t, geo);
     } else {
-        if (!workspace) { set_error("p6d_pose_loss_fwd_bwd: workspace required for B > %d", SMALL_B); return P6D_EINVAL; }
+        if (!workspace) { set_error("pose loss: workspace required for B > %d", SMALL_B); return P6D_EINVAL; }
         int sms = 0;
         P6D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         int64_t blocks = (B + LOSS_T - 1) / LOSS_T;
@@ -233,10 +270,35 @@ int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, con
         if (blocks > cap) blocks = cap;
         pose_loss_large_kernel<<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
                                                                     mode, out, grad_q, grad_t,
-                                                                    static_cast<Workspace*>(workspace));
+                                                                    static_cast<Workspace*>(workspace), geo);
     }
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;
+}
+
+int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, const float* gt, int64_t B,
+                          float rot_weight, float trans_weight, int mode, float* out, float* grad_q,
+                          float* grad_t, void* workspace, int device, void* stream) {
+    if (B <= 0 || !pq || !pt || !gq || !gt || !out || (mode != 0 && mode != 1)) {
+        set_error("p6d_pose_loss_fwd_bwd: bad arguments (B=%lld, mode=%d)", (long long)B, mode);
+        return P6D_EINVAL;
+    }
+    Geo geo{};
+    return launch_pose_loss(pq, pt, gq, gt, B, rot_weight, trans_weight, mode, out, grad_q, grad_t, workspace,
+                            device, stream, geo);
+}
+
+int p6d_pose_loss_pinhole_fwd_bwd(const float* pq, const float* z, const float* uv, const float* K, int k_batched,
+                                  const float* gq, const float* gt, int64_t B, float rot_weight,
+                                  float trans_weight, int mode, float* out, float* grad_q, float* grad_z,
+                                  float* trans_out, void* workspace, int device, void* stream) {
+    if (B <= 0 || !pq || !z || !uv || !K || !gq || !gt || !out || (mode != 0 && mode != 1)) {
+        set_error("p6d_pose_loss_pinhole_fwd_bwd: bad arguments (B=%lld, mode=%d)", (long long)B, mode);
+        return P6D_EINVAL;
+    }
+    Geo geo{z, uv, K, k_batched, grad_z, trans_out};
+    return launch_pose_loss(pq, nullptr, gq, gt, B, rot_weight, trans_weight, mode, out, grad_q, nullptr, workspace,
+                            device, stream, geo);
 }
 
 }  // extern "C"

@@ -74,6 +74,51 @@ class _FusedPoseLoss(torch.autograd.Function):
         return dq, dt, None, None, None, None, None, None
 
 
+class _FusedGeometricPoseLoss(torch.autograd.Function):
+    """PoseLoss on a pinhole translation computed in the same launch (kernels d1 + c):
+    returns (loss, translation); gradients flow to pred_rot and z_pred."""
+
+    @staticmethod
+    def forward(ctx, pred_rot, z_pred, bbox_center, camera_matrix, gt_rot, gt_trans, rot_weight, trans_weight, mode):
+        core = _core()
+        dev = core.require_cuda(pred_rot.device)
+        pq = core.as_cuda_f32(pred_rot, dev, (4,))
+        z = core.as_cuda_f32(z_pred, dev, ())
+        uv = core.as_cuda_f32(bbox_center, dev, (2,))
+        gq = core.as_cuda_f32(gt_rot, dev, (4,))
+        gt = core.as_cuda_f32(gt_trans, dev, (3,))
+        B = pq.shape[0]
+        if B == 0 or not (z.shape[0] == uv.shape[0] == gq.shape[0] == gt.shape[0] == B):
+            raise ValueError("forward_geometric needs non-empty inputs with a common batch dimension")
+        K = core.as_cuda_f32(camera_matrix, dev, ())
+        if camera_matrix.dim() == 2 and K.numel() == 9:
+            kb = 0
+        elif camera_matrix.dim() == 3 and K.numel() == 9 * B:
+            kb = 1
+        else:
+            raise ValueError("camera_matrix must be [3,3] or [B,3,3]")
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        trans = torch.empty(B, 3, dtype=torch.float32, device=dev)
+        gq_out = torch.empty_like(pq) if ctx.needs_input_grad[0] else None
+        gz_out = torch.empty(B, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        core.check(core.lib().p6d_pose_loss_pinhole_fwd_bwd(
+            core.ptr(pq), core.ptr(z), core.ptr(uv), core.ptr(K), kb, core.ptr(gq), core.ptr(gt), B,
+            float(rot_weight), float(trans_weight), int(mode), core.ptr(out), core.ptr(gq_out), core.ptr(gz_out),
+            core.ptr(trans), core.ptr(_workspace(dev)), dev.index, core.stream_ptr(dev)))
+        ctx.grads = (gq_out, gz_out)
+        ctx.meta = (pred_rot.shape, z_pred.shape, pred_rot.dtype, z_pred.dtype)
+        ctx.mark_non_differentiable(trans)
+        return out[0].clone(), trans
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_trans):
+        gq, gz = ctx.grads
+        rs, zs, rd, zd = ctx.meta
+        dq = (gq * grad_loss).reshape(rs).to(rd) if gq is not None else None
+        dz = (gz * grad_loss).reshape(zs).to(zd) if gz is not None else None
+        return dq, dz, None, None, None, None, None, None, None
+
+
 class PoseLoss(nn.Module):
     """rot_weight * rotation_loss + trans_weight * L1(translation)  (reference :8-65)."""
 
@@ -90,6 +135,15 @@ class PoseLoss(nn.Module):
     def forward(self, pred_rot, pred_trans, gt_rot, gt_trans, obj_ids=None):
         return _FusedPoseLoss.apply(pred_rot, pred_trans, gt_rot, gt_trans, self.rot_weight,
                                     self.trans_weight, self._mode(), 0)
+
+    def forward_geometric(self, pred_rot, z_pred, bbox_center, camera_matrix, gt_rot, gt_trans):
+        """The RGB-Geometric training step in one launch (addition to the reference surface):
+        equals ``self(pred_rot, pinhole_translation(z_pred, bbox_center, camera_matrix), gt_rot,
+        gt_trans)`` bit for bit -- the model's pinhole translation
+        (reference models/pose_net_rgb_geometric.py:93-109) is computed inside the loss kernel
+        and the gradient comes back w.r.t. ``z_pred``.  Returns (loss, translation [B,3])."""
+        return _FusedGeometricPoseLoss.apply(pred_rot, z_pred, bbox_center, camera_matrix, gt_rot, gt_trans,
+                                             self.rot_weight, self.trans_weight, self._mode())
 
     def _rotation_only(self, q1, q2, mode):
         zeros = torch.zeros(q1.shape[0], 3, dtype=torch.float32, device=q1.device)

@@ -141,6 +141,16 @@ int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, con
                           int64_t B, float rot_weight, float trans_weight, int mode, float* out,
                           float* grad_q, float* grad_t, void* workspace, int device, void* stream);
 
+/* The RGB-Geometric training step in ONE launch: kernel (d1) fused into kernel (c).
+ * pred_trans is computed in-kernel from (z [B], uv [B,2], K) exactly like p6d_pinhole_fwd
+ * (models/pose_net_rgb_geometric.py:93-109) and the loss gradient is returned w.r.t. z
+ * (grad_z [B], nullable) exactly like p6d_pinhole_bwd applied to d loss / d pred_trans.
+ * trans_out [B,3] (nullable) receives the translation.  Other arguments as above. */
+int p6d_pose_loss_pinhole_fwd_bwd(const float* pq, const float* z, const float* uv, const float* K, int k_batched,
+                                  const float* gq, const float* gt, int64_t B, float rot_weight,
+                                  float trans_weight, int mode, float* out, float* grad_q, float* grad_z,
+                                  float* trans_out, void* workspace, int device, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Pinhole XY from bbox centre and predicted Z
  * (PoseNetRGBGeometric._compute_pinhole_translation, models/pose_net_rgb_geometric.py:93-109).

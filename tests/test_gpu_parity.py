@@ -301,6 +301,30 @@ def test_training_step_chain_rgb_geometric(pkg, cuda_dev):
     assert np.all(np.abs(got[finite] - ref[finite]) <= 2e-5 * scale)
 
 
+def test_fused_geometric_training_step(pkg, cuda_dev, W):
+    """(d1) fused into (c): one launch == pinhole_translation + PoseLoss, bit for bit, for the
+    loss, the translation and the gradients w.r.t. rot and z (small and multi-CTA batch)."""
+    for B, mode in ((32, "geodesic"), (32, "l1"), (5000, "geodesic")):
+        c = W.config3(B, 3)
+        crit = pkg.PoseLoss(1.0, 10.0, mode)
+        for Kt in (T(c["K"], cuda_dev), T(c["K"][0], cuda_dev)):
+            r1 = T(c["rot_raw"], cuda_dev).requires_grad_(True); z1 = T(c["z_pred"], cuda_dev).requires_grad_(True)
+            t1 = pkg.pinhole_translation(z1, T(c["bbox_center"], cuda_dev), Kt)
+            l1 = crit(r1, t1, T(c["gt_rot"], cuda_dev), T(c["gt_trans"], cuda_dev))
+            (1.5 * l1).backward()
+            r2 = T(c["rot_raw"], cuda_dev).requires_grad_(True); z2 = T(c["z_pred"], cuda_dev).requires_grad_(True)
+            l2, t2 = crit.forward_geometric(r2, z2, T(c["bbox_center"], cuda_dev), Kt, T(c["gt_rot"], cuda_dev),
+                                            T(c["gt_trans"], cuda_dev))
+            (1.5 * l2).backward()
+            assert same_bits(t2.cpu().numpy(), t1.detach().cpu().numpy())
+            assert same_bits(r2.grad.cpu().numpy(), r1.grad.cpu().numpy())
+            assert same_bits(z2.grad.cpu().numpy(), z1.grad.cpu().numpy()) and z2.grad.shape == (B, 1)
+            if B <= 2048:
+                assert l2.item() == l1.item()
+            else:   # float64 atomics: summation order of the block partials is not fixed
+                assert abs(l2.item() - l1.item()) <= 1e-6 * abs(l1.item())
+
+
 def test_pose_loss_weights_large_batch_and_no_grad(pkg, cuda_dev, W, oracle):
     g = load_golden("pose_loss_cfg3")
     a = T(g["rot_raw"], cuda_dev).requires_grad_(True)

@@ -133,3 +133,35 @@ def test_workloads_are_deterministic(W):
     g = load_golden("eval_cfg1")
     pts, dia, poses = W.config1(seed=1)
     assert np.array_equal(pts[0], g["mesh_0"]) and np.array_equal(poses[0], g["pq"])
+
+
+def test_dropin_launcher_merges_reference_packages(tmp_path):
+    """dropin.install(): hot-path modules from this repo, everything else from a reference
+    tree that inserts itself at sys.path[0] (like the reference's scripts do)."""
+    import subprocess, sys
+    ref = tmp_path / "ref"
+    (ref / "models").mkdir(parents=True); (ref / "utils").mkdir(); (ref / "scripts").mkdir()
+    (ref / "models" / "__init__.py").write_text("")
+    (ref / "models" / "add_loss.py").write_text("class ADDLoss: ORIGIN = 'reference'\n")
+    (ref / "models" / "pose_net_rgb.py").write_text("class PoseNetRGB: ORIGIN = 'reference'\n")
+    (ref / "models" / "pose_net_rgb_geometric.py").write_text(
+        "class PoseNetRGBGeometric:\n    def _compute_pinhole_translation(self, z, c, K): return 'reference'\n")
+    (ref / "models" / "pose_net_rgbd_geometric.py").write_text(
+        "class PoseNetRGBDGeometric:\n    def _compute_pinhole_translation(self, d, c, K): return 'reference'\n")
+    (ref / "utils" / "__init__.py").write_text("")
+    (ref / "utils" / "mesh_utils.py").write_text("def load_mesh_corners(p): return 'reference'\n")
+    (ref / "utils" / "visualization.py").write_text(
+        "def project_points(*a): return 'reference'\ndef draw_3d_box(*a): pass\ndef draw_axes(*a): pass\n")
+    (ref / "scripts" / "s.py").write_text(
+        "import os, sys\nPROJECT_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))\n"
+        "sys.path.insert(0, PROJECT_ROOT)\n"
+        "from models.add_loss import ADDLoss\nfrom models.pose_loss import PoseLoss\n"
+        "from models.pose_net_rgb import PoseNetRGB\nfrom models.pose_net_rgb_geometric import PoseNetRGBGeometric\n"
+        "from utils.mesh_utils import load_mesh_corners\nfrom utils.visualization import project_points\n"
+        "from utils.camera import DEFAULT_K\nfrom utils import draw_3d_box\n"
+        "print(ADDLoss.__module__, getattr(ADDLoss, 'ORIGIN', 'b200'), PoseNetRGB.ORIGIN, load_mesh_corners(0),"
+        " PoseNetRGBGeometric._compute_pinhole_translation.__name__, float(DEFAULT_K[1, 1]))\n")
+    launcher = os.path.join(REPO, "6d-pose-estimation_b200", "dropin.py")
+    out = subprocess.run([sys.executable, launcher, str(ref), "scripts/s.py"], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["models.add_loss", "b200", "reference", "reference", "<lambda>", "573.57043"]
