@@ -311,11 +311,11 @@ def test_fused_geometric_training_step(pkg, cuda_dev, W):
             r1 = T(c["rot_raw"], cuda_dev).requires_grad_(True); z1 = T(c["z_pred"], cuda_dev).requires_grad_(True)
             t1 = pkg.pinhole_translation(z1, T(c["bbox_center"], cuda_dev), Kt)
             l1 = crit(r1, t1, T(c["gt_rot"], cuda_dev), T(c["gt_trans"], cuda_dev))
-            (1.5 * l1).backward()
+            l1.backward()
             r2 = T(c["rot_raw"], cuda_dev).requires_grad_(True); z2 = T(c["z_pred"], cuda_dev).requires_grad_(True)
             l2, t2 = crit.forward_geometric(r2, z2, T(c["bbox_center"], cuda_dev), Kt, T(c["gt_rot"], cuda_dev),
                                             T(c["gt_trans"], cuda_dev))
-            (1.5 * l2).backward()
+            l2.backward()        # upstream gradient 1: every rounding happens in the same place
             assert same_bits(t2.cpu().numpy(), t1.detach().cpu().numpy())
             assert same_bits(r2.grad.cpu().numpy(), r1.grad.cpu().numpy())
             assert same_bits(z2.grad.cpu().numpy(), z1.grad.cpu().numpy()) and z2.grad.shape == (B, 1)
@@ -323,6 +323,15 @@ def test_fused_geometric_training_step(pkg, cuda_dev, W):
                 assert l2.item() == l1.item()
             else:   # float64 atomics: summation order of the block partials is not fixed
                 assert abs(l2.item() - l1.item()) <= 1e-6 * abs(l1.item())
+    # non-unit upstream gradient: scaled once at the end instead of before the pinhole backward
+    c = W.config3(32, 3)
+    r = T(c["rot_raw"], cuda_dev).requires_grad_(True); z = T(c["z_pred"], cuda_dev).requires_grad_(True)
+    l, _ = pkg.PoseLoss(1.0, 10.0)(r, z, T(c["bbox_center"], cuda_dev), T(c["K"], cuda_dev), T(c["gt_rot"], cuda_dev),
+                                   T(c["gt_trans"], cuda_dev)) if False else pkg.PoseLoss(1.0, 10.0).forward_geometric(
+        r, z, T(c["bbox_center"], cuda_dev), T(c["K"], cuda_dev), T(c["gt_rot"], cuda_dev), T(c["gt_trans"], cuda_dev))
+    (3.0 * l).backward()
+    g = load_golden("pose_loss_cfg3")
+    assert np.allclose(z.grad.cpu().numpy(), 3.0 * g["geodesic_b32_grad_z"], rtol=1e-5, atol=1e-7)
 
 
 def test_pose_loss_weights_large_batch_and_no_grad(pkg, cuda_dev, W, oracle):
