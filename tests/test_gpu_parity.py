@@ -326,9 +326,8 @@ def test_fused_geometric_training_step(pkg, cuda_dev, W):
     # non-unit upstream gradient: scaled once at the end instead of before the pinhole backward
     c = W.config3(32, 3)
     r = T(c["rot_raw"], cuda_dev).requires_grad_(True); z = T(c["z_pred"], cuda_dev).requires_grad_(True)
-    l, _ = pkg.PoseLoss(1.0, 10.0)(r, z, T(c["bbox_center"], cuda_dev), T(c["K"], cuda_dev), T(c["gt_rot"], cuda_dev),
-                                   T(c["gt_trans"], cuda_dev)) if False else pkg.PoseLoss(1.0, 10.0).forward_geometric(
-        r, z, T(c["bbox_center"], cuda_dev), T(c["K"], cuda_dev), T(c["gt_rot"], cuda_dev), T(c["gt_trans"], cuda_dev))
+    l, _ = pkg.PoseLoss(1.0, 10.0).forward_geometric(r, z, T(c["bbox_center"], cuda_dev), T(c["K"], cuda_dev),
+                                                     T(c["gt_rot"], cuda_dev), T(c["gt_trans"], cuda_dev))
     (3.0 * l).backward()
     g = load_golden("pose_loss_cfg3")
     assert np.allclose(z.grad.cpu().numpy(), 3.0 * g["geodesic_b32_grad_z"], rtol=1e-5, atol=1e-7)
