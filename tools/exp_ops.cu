@@ -31,7 +31,23 @@ template <int MODE> __global__ void __launch_bounds__(T) k(float* out, int iters
                 else if (MODE == 6) { asm volatile("mul.rn.f32 %0, %0, %1;" : "+f"(v[i].x) : "f"(a)); }
                 else if (MODE == 9) v[i] = fma2(v[i], v[i], bb);
             }
-            if (MODE == 7 || MODE == 8) {
+            if (MODE >= 12 && MODE <= 20) {
+                // issue-port probe: 16 independent packed FMAs interleaved with R independent non-FMA ops each
+#pragma unroll
+                for (int i = 0; i < C; ++i) {
+                    v[i] = fma2(v[i], aa, bb);
+                    if (MODE == 12) { asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(b)); }
+                    if (MODE == 13) { asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(b)); asm volatile("max.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(a)); }
+                    if (MODE == 14) { int t = __float_as_int(m[i]); asm volatile("add.s32 %0, %0, 3;" : "+r"(t)); m[i] = __int_as_float(t); }
+                    if (MODE == 15 && (i & 1) == 0) { asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(b)); }
+                    if (MODE == 16 && (i & 3) == 0) { asm volatile("min.f32 %0, %0, %1;" : "+f"(m[i]) : "f"(b)); }
+                    if (MODE == 17) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(m[i]) : "f"(b), "f"(a)); }
+                    if (MODE == 18) { int t = __float_as_int(m[i]); asm volatile("min.s32 %0, %0, %1;" : "+r"(t) : "r"(it + i)); m[i] = __int_as_float(t); }
+                    if (MODE == 19) { m[i] = __int_as_float(__vimin3_s32(__float_as_int(m[i]), it + i, j - i)); }
+                    if (MODE == 20) { m[i] = __uint_as_float(__vimin3_u32(__float_as_uint(m[i]), (unsigned)(it + i), (unsigned)(j + i))); }
+                }
+            }
+            if (MODE == 7 || MODE == 8 || MODE == 21 || MODE == 22) {
                 // 8 "pred points" (scalars m-independent) x 1 half-quad whose gt operand is v[j&15] (changes every j)
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk) {
@@ -41,6 +57,8 @@ template <int MODE> __global__ void __launch_bounds__(T) k(float* out, int iters
                     float2 dz = sub2(make_float2(pz, pz), v[(j + 2) & 15]);
                     float2 s = mul2(dx, dx); s = fma2(dy, dy, s); s = fma2(dz, dz, s);
                     if (MODE == 8) m[kk] = min3(m[kk], s.x, s.y);
+                    else if (MODE == 21) m[kk] = __int_as_float(__vimin3_s32(__float_as_int(m[kk]), __float_as_int(s.x), __float_as_int(s.y)));
+                    else if (MODE == 22) m[kk] = __uint_as_float(__vimin3_u32(__float_as_uint(m[kk]), __float_as_uint(s.x), __float_as_uint(s.y)));
                     else m[kk] = s.x;
                 }
                 v[j & 15].x += 1.0f;  // keep the operands changing
@@ -96,6 +114,17 @@ int main() {
     run<1>("FADD2 packed-packed", C, d, sms); run<2>("FADD2 scalar-bcast - packed", C, d, sms); run<3>("FMUL2", C, d, sms);
     run<7>("tile 3xFADD2+FMUL2+2xFFMA2 (48 per inner)", 48, d, sms);
     run<8>("tile + FMNMX3 (48 FMA-pipe per inner)", 48, d, sms);
+    run<12>("FFMA2 + 1 indep FMNMX per FFMA2", C, d, sms);
+    run<13>("FFMA2 + 2 indep FMNMX per FFMA2", C, d, sms);
+    run<14>("FFMA2 + 1 indep IADD per FFMA2", C, d, sms);
+    run<15>("FFMA2 + 1 FMNMX per 2 FFMA2", C, d, sms);
+    run<16>("FFMA2 + 1 FMNMX per 4 FFMA2", C, d, sms);
+    run<17>("FFMA2 + 1 indep FMNMX3 per FFMA2", C, d, sms);
+    run<18>("FFMA2 + 1 indep IMNMX (s32) per FFMA2", C, d, sms);
+    run<19>("FFMA2 + 1 indep VIMNMX3 (s32) per FFMA2", C, d, sms);
+    run<20>("FFMA2 + 1 indep VIMNMX3.U32 per FFMA2", C, d, sms);
+    run<21>("tile + VIMNMX3 s32 (48 FMA-pipe per inner)", 48, d, sms);
+    run<22>("tile + VIMNMX3 u32 (48 FMA-pipe per inner)", 48, d, sms);
     run<10>("SCALAR tile + FMNMX3 (96 FMA-pipe per inner)", 96, d, sms);
     run<11>("SCALAR tile + 2xFMNMX (96 per inner)", 96, d, sms);
     return 0;
