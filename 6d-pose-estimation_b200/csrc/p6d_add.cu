@@ -450,28 +450,44 @@ static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_
         if (launches) ++*launches;
         return P6D_OK;
     }
-    int limit = 0;
-    int rc = max_optin_smem(t->device, &limit);
-    if (rc) return rc;
     const size_t smem = adds_smem_bytes(t->max_count);
-    if (smem + 256 > static_cast<size_t>(limit)) {
-        set_error("largest mesh has %d points; the ADD-S kernel holds the mesh, the gt cloud and two "
-                  "distance rows in shared memory and accepts at most %d points on this device",
-                  t->max_count, adds_max_points_for(limit));
-        return P6D_ETOOBIG;
+    const int vi = adds_variant(t->max_count);
+    const AddsVariant& var = g_adds_variants[vi];
+    if (t->adds_ready_variant != vi) {
+        int limit = 0;
+        int rc = max_optin_smem(t->device, &limit);
+        if (rc) return rc;
+        if (smem + 256 > static_cast<size_t>(limit)) {
+            set_error("largest mesh has %d points; the ADD-S kernel holds the mesh, the gt cloud and two "
+                      "distance rows in shared memory and accepts at most %d points on this device",
+                      t->max_count, adds_max_points_for(limit));
+            return P6D_ETOOBIG;
+        }
+        // the attribute is a per-device maximum shared by every table: only ever raise it
+        static size_t raised[64][N_ADDS_VARIANTS] = {};
+        size_t& cur = raised[t->device & 63][vi];
+        if (smem > cur) {
+            P6D_CUDA(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            cur = smem;
+        }
+        int occ = 0;
+        P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var.fn, var.threads, smem));
+        t->adds_per_sm = occ < 1 ? 1 : occ;
+        t->adds_ready_variant = vi;
     }
-    const AddsVariant& var = g_adds_variants[adds_variant(t->max_count)];
-    P6D_CUDA(cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 0;
-    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, var.fn, var.threads, smem));
-    if (per_sm < 1) per_sm = 1;
+    const int per_sm = t->adds_per_sm;
     int64_t grid = static_cast<int64_t>(t->sm_count) * per_sm;
     if (grid > args.B) grid = args.B;
     EvalArgs a2 = args;
     {
-        const char* e = getenv("P6D_DEBUG_SCAN_REPS");
-        a2.scan_reps = e ? atoi(e) : 1;
-        if (a2.scan_reps < 1) a2.scan_reps = 1;
+        // measurement knob (tools/variants.py): repeat the all-pairs scan to isolate its rate
+        static int reps = 0;
+        if (reps == 0) {
+            const char* e = getenv("P6D_DEBUG_SCAN_REPS");
+            reps = e ? atoi(e) : 1;
+            if (reps < 1) reps = 1;
+        }
+        a2.scan_reps = reps;
     }
     a2.work_counter = t->d_counters + (t->counter_idx++ % P6D_NUM_COUNTERS);
     P6D_CUDA(cudaMemsetAsync(a2.work_counter, 0, sizeof(int), st));

@@ -445,3 +445,18 @@ def test_depth_crop_backproject_fused(pkg, cuda_dev, W, oracle):
     xyz2 = pkg.depth_crop_backproject(depth2, boxes2, K)
     assert same_bits(xyz2.cpu().numpy(), r["xyz"])
     assert pkg.depth_crop_backproject(depth2, boxes2[:0], K).shape == (0, 3)
+
+
+def test_two_tables_of_different_size_interleaved(pkg, cuda_dev, W, oracle):
+    """The ADD-S kernel's shared-memory attribute is per device, not per table: a small and a
+    large table used alternately must both keep launching (and keep their results)."""
+    small = ({0: W.sphere_mesh(1200, 0.1, 1)}, {0: 0.1})
+    big = ({0: W.sphere_mesh(4000, 0.1, 2)}, {0: 0.1})
+    pq, pt, gq, gt = W.random_poses(6, 3)
+    obj = np.zeros(6, np.int64)
+    crits = [make_crit(pkg, *small, cuda_dev), make_crit(pkg, *big, cuda_dev)]
+    refs = [oracle.add_eval(oracle.MeshTable(*m), pq, pt, gq, gt, obj, n_threads=4) for m in (small, big)]
+    for _ in range(2):
+        for crit, ref in zip(crits, refs):
+            got = crit.eval_poses(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
+            assert same_bits(got["add_s"], ref[1]) and same_bits(got["add"], ref[0])
