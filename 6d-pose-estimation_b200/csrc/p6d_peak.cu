@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(PK_T) peak_ffma2_kernel(float* out, int iters,
 }
 
 constexpr int MIX_K = 8;
-constexpr int MIX_INNER = 32;
+constexpr int MIX_INNER = 16;   // 16 tiles x 56 instructions = 14 KB of code: stays inside the 32 KB instruction cache
 
 // volatile forms: keep the program order of the tile (the scheduler of the non-volatile forms
 // interleaves differently and measures ~10 % lower)
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(PK_T) peak_mix_kernel(float* out, int iters, f
         m[k] = 3.0e38f;
         qx[k] = a + k; qy[k] = b - k; qz[k] = a * k;   // the "pred points", register-resident like in the kernel
     }
+#pragma unroll 1
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int j = 0; j < MIX_INNER; ++j) {

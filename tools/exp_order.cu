@@ -8,6 +8,7 @@
 #define MUL2(r, a) asm volatile("{.reg .b64 ra, rc; mov.b64 ra, {%2,%3}; mul.rn.f32x2 rc, ra, ra; mov.b64 {%0,%1}, rc;}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y))
 #define FMA2(r, a) asm volatile("{.reg .b64 ra, rc; mov.b64 ra, {%2,%3}; mov.b64 rc, {%0,%1}; fma.rn.f32x2 rc, ra, ra, rc; mov.b64 {%0,%1}, rc;}" : "+f"(r.x), "+f"(r.y) : "f"(a.x), "f"(a.y))
 #define MIN3(m, s) asm volatile("min.NaN.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(s.x), "f"(s.y))
+#define MIN2(m, v) asm volatile("min.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(v))
 
 // ORDER 0: per pred point: sub,sub,sub,mul,fma,fma,min      (the library kernel's source order)
 // ORDER 1: by plane: all subs, all muls, all fmas, all mins
@@ -18,9 +19,10 @@ __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__
     extern __shared__ float4 sm[];
     for (int i = threadIdx.x; i < 3 * nquads; i += T) sm[i] = reinterpret_cast<const float4*>(g)[i];
     __syncthreads();
-    float px[K], py[K], pz[K], m[K];
+    float px[K], py[K], pz[K], m[K], m2[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
+        m2[k] = 3.0e38f;
         px[k] = g[(threadIdx.x * K + k) % (4 * nquads)];
         py[k] = g[(threadIdx.x * K + k + 7) % (4 * nquads)] * 0.5f;
         pz[k] = g[(threadIdx.x * K + k + 13) % (4 * nquads)] * 0.25f;
@@ -69,6 +71,24 @@ __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__
                     for (int k = 0; k < K; ++k) { MIN3(m[k], pend[k]); }
 #pragma unroll
                     for (int k = 0; k < K; ++k) { MUL2(s[k], dx[k]); FMA2(s[k], dy[k]); FMA2(s[k], dz[k]); pend[k] = s[k]; }
+                } else if (ORDER == 4) {
+                    // two 2-input minima on separate accumulators (cannot fuse into FMNMX3), each placed
+                    // right behind a FADD2 of the same warp (FMNMX is free next to FADD2/FMUL2, costs a
+                    // full cycle next to FFMA2: tools/exp_pair.cu)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        SUB2(dx[k], px[k], gx); MIN2(m[k], pend[k].x); SUB2(dy[k], py[k], gy); MIN2(m2[k], pend[k].y);
+                        SUB2(dz[k], pz[k], gz);
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) { MUL2(s[k], dx[k]); FMA2(s[k], dy[k]); FMA2(s[k], dz[k]); pend[k] = s[k]; }
+                } else if (ORDER == 5) {
+                    // same two accumulators, but in the library kernel's per-point order (no deferral)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        SUB2(dx[k], px[k], gx); SUB2(dy[k], py[k], gy); SUB2(dz[k], pz[k], gz);
+                        MUL2(s[k], dx[k]); FMA2(s[k], dy[k]); FMA2(s[k], dz[k]); MIN2(m[k], s[k].x); MIN2(m2[k], s[k].y);
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < K; ++k) { SUB2(dx[k], px[k], gx); MIN3(m[k], pend[k]); SUB2(dy[k], py[k], gy); SUB2(dz[k], pz[k], gz); }
@@ -80,6 +100,8 @@ __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__
 #pragma unroll
         for (int k = 0; k < K; ++k) MIN3(m[k], pend[k]);
     }
+#pragma unroll
+    for (int k = 0; k < K; ++k) MIN2(m[k], m2[k]);
     float s = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) s += m[k];
@@ -122,6 +144,10 @@ int main() {
     run<512, 4, 2, 1>("K4 plane order", d_g, d_out, nquads, reps, sms);
     run<512, 4, 2, 2>("K4 deferred mins", d_g, d_out, nquads, reps, sms);
     run<512, 4, 2, 3>("K4 mins among subs", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 4>("K4 2xFMNMX behind FADD2", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 5>("K4 2xFMNMX per-point", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 4>("K8 2xFMNMX behind FADD2", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 5>("K8 2xFMNMX per-point", d_g, d_out, nquads, reps, sms);
     run<256, 8, 2, 0>("K8 per-point order", d_g, d_out, nquads, reps, sms);
     run<256, 8, 2, 1>("K8 plane order", d_g, d_out, nquads, reps, sms);
     run<256, 8, 2, 2>("K8 deferred mins", d_g, d_out, nquads, reps, sms);
