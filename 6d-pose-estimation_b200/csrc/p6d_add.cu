@@ -79,7 +79,21 @@ __device__ __forceinline__ void accumulate(const EvalArgs& a, int64_t oid, bool 
     if (a.acc.adds_sum && has_adds) atomicAdd(a.acc.adds_sum + oid, static_cast<double>(adds));
 }
 
-__global__ void __launch_bounds__(ADD_WARPS * 32) add_warp_kernel(EvalArgs a) {
+template <int MODE>
+__device__ __forceinline__ float add_mean_of_pose(const float* __restrict__ mx, int np, int n, const float* Rp,
+                                                  const float* tp, const float* Rg, const float* tg, int lane) {
+    auto dist = [&](int e) -> float {
+        const float* p = mx + e;
+        const float x = __ldg(p), y = __ldg(p + np), z = __ldg(p + 2 * np);
+        const float px = xform_coord<MODE>(x, y, z, Rp + 0, tp[0]), gx = xform_coord<MODE>(x, y, z, Rg + 0, tg[0]);
+        const float py = xform_coord<MODE>(x, y, z, Rp + 3, tp[1]), gy = xform_coord<MODE>(x, y, z, Rg + 3, tg[1]);
+        const float pz = xform_coord<MODE>(x, y, z, Rp + 6, tp[2]), gz = xform_coord<MODE>(x, y, z, Rg + 6, tg[2]);
+        return __fsqrt_rn(sq3(__fsub_rn(px, gx), __fsub_rn(py, gy), __fsub_rn(pz, gz)));
+    };
+    return aten_mean_warp(dist, n, lane);
+}
+
+__global__ void __launch_bounds__(ADD_WARPS * 32, 3) add_warp_kernel(EvalArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = static_cast<int64_t>(blockIdx.x) * ADD_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = static_cast<int64_t>(gridDim.x) * ADD_WARPS;
@@ -97,8 +111,6 @@ __global__ void __launch_bounds__(ADD_WARPS * 32) add_warp_kernel(EvalArgs a) {
         }
         const SlotInfo s = a.slots[oid];
         const float* mx = a.soa + s.soa_offset;
-        const float* my = mx + s.padded;
-        const float* mz = my + s.padded;
         float Rp[9], Rg[9], tp[3], tg[3], q[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) q[k] = __ldg(a.pq + 4 * b + k);
@@ -111,15 +123,12 @@ __global__ void __launch_bounds__(ADD_WARPS * 32) add_warp_kernel(EvalArgs a) {
             tp[k] = __ldg(a.pt + 3 * b + k);
             tg[k] = __ldg(a.gt + 3 * b + k);
         }
-        const int mode = s.xform_mode;
-        auto dist = [&](int e) -> float {
-            const float x = __ldg(mx + e), y = __ldg(my + e), z = __ldg(mz + e);
-            float px, py, pz, gx, gy, gz;
-            xform_point(mode, x, y, z, Rp, tp, px, py, pz);
-            xform_point(mode, x, y, z, Rg, tg, gx, gy, gz);
-            return __fsqrt_rn(sq3(__fsub_rn(px, gx), __fsub_rn(py, gy), __fsub_rn(pz, gz)));
-        };
-        const float mean = aten_mean_warp(dist, s.count, lane);
+        // the torch.mm rounding mode depends only on the mesh size: dispatch once per pose so that
+        // the per-point code is branch-free
+        float mean;
+        if (s.xform_mode == XF_FMA_CHAIN) mean = add_mean_of_pose<XF_FMA_CHAIN>(mx, s.padded, s.count, Rp, tp, Rg, tg, lane);
+        else if (s.xform_mode == XF_N1) mean = add_mean_of_pose<XF_N1>(mx, s.padded, s.count, Rp, tp, Rg, tg, lane);
+        else mean = add_mean_of_pose<XF_SMALL>(mx, s.padded, s.count, Rp, tp, Rg, tg, lane);
         if (lane == 0) {
             const bool is_hit = static_cast<double>(mean) < s.threshold;
             a.add[b] = mean;
