@@ -209,22 +209,8 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq
                                                                  int mode, float* out, float* grad_q,
                                                                  float* grad_t, Workspace* ws, Geo geo) {
     double rs = 0.0, ts = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * LOSS_T;
-    for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += stride) {
-        // the row math is long (IEEE divisions, atan2f): pull the next row of this thread towards
-        // L1 now so that its loads do not start only after this row is finished
-        const int64_t bn = b + stride;
-        if (bn < B) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pq + 4 * bn));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(gq + 4 * bn));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(gt + 3 * bn));
-            if (geo.z) {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(geo.uv + 2 * bn));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(geo.z + bn));
-            } else {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pt + 3 * bn));
-            }
-        }
+    // (prefetching the next row of the thread with prefetch.global.L1 was tried: 10 % slower)
+    for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * LOSS_T) {
         const RowOut o = loss_row_any(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         rs += (double)o.rot;
         ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
