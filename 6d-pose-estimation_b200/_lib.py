@@ -31,6 +31,7 @@ EXPORTS = (
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
     "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject", "p6d_fp32_microbench",
     "p6d_adds_timeline", "p6d_add_backward", "p6d_depth_crop_backproject", "p6d_pose_loss_pinhole_fwd_bwd",
+    "p6d_project_points",
 )
 
 
@@ -87,6 +88,7 @@ def lib() -> C.CDLL:
     L.p6d_depth_backproject.argtypes = [vp, i32, i32, vp, vp, i32, i64, f32, vp, i32, vp]
     L.p6d_fp32_microbench.argtypes = [i32, i32, i32, C.POINTER(f64), C.POINTER(f64)]
     L.p6d_depth_crop_backproject.argtypes = [vp, i32, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp]
+    L.p6d_project_points.argtypes = [vp, i32, vp, i32, vp, vp, i64, vp, i32, vp]
     L.p6d_add_backward.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, f32, vp, vp, vp]
     L.p6d_adds_timeline.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
     missing = [n for n in EXPORTS if not hasattr(L, n)]

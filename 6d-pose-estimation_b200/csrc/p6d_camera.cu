@@ -172,6 +172,41 @@ __global__ void __launch_bounds__(CAM_T) depth_crop_backproject_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------
+// N4: utils/visualization.project_points for B poses (float64 like the reference's NumPy).
+__global__ void __launch_bounds__(CAM_T) project_points_kernel(const double* __restrict__ pts, int N,
+                                                               const double* __restrict__ rot, int is_quat,
+                                                               const double* __restrict__ tr,
+                                                               const double* __restrict__ K, int64_t B,
+                                                               long long* __restrict__ uv) {
+    const double fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+    const int64_t total = B * N;
+    for (int64_t i = (int64_t)blockIdx.x * CAM_T + threadIdx.x; i < total; i += (int64_t)gridDim.x * CAM_T) {
+        const int64_t b = i / N;
+        const int n = (int)(i - b * N);
+        double R[9];
+        if (is_quat) {
+            // scipy Rotation.from_quat: normalise, then the homogeneous formula
+            double x = rot[4 * b], y = rot[4 * b + 1], z = rot[4 * b + 2], w = rot[4 * b + 3];
+            const double nrm = sqrt(x * x + y * y + z * z + w * w);
+            x /= nrm; y /= nrm; z /= nrm; w /= nrm;
+            R[0] = x * x - y * y - z * z + w * w; R[1] = 2 * (x * y - z * w); R[2] = 2 * (x * z + y * w);
+            R[3] = 2 * (x * y + z * w); R[4] = -x * x + y * y - z * z + w * w; R[5] = 2 * (y * z - x * w);
+            R[6] = 2 * (x * z - y * w); R[7] = 2 * (y * z + x * w); R[8] = -x * x - y * y + z * z + w * w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) R[k] = rot[9 * b + k];
+        }
+        const double px = pts[3 * n], py = pts[3 * n + 1], pz = pts[3 * n + 2];
+        const double X = R[0] * px + R[1] * py + R[2] * pz + tr[3 * b];
+        const double Y = R[3] * px + R[4] * py + R[5] * pz + tr[3 * b + 1];
+        double Z = R[6] * px + R[7] * py + R[8] * pz + tr[3 * b + 2];
+        Z = Z < 0.001 ? 0.001 : Z;                    // np.clip(z, 0.001, None)
+        uv[2 * i] = (long long)(X * fx / Z + cx);     // .astype(int): truncation toward zero
+        uv[2 * i + 1] = (long long)(Y * fy / Z + cy);
+    }
+}
+
 static int grid_for(int64_t B, int device, unsigned* grid) {
     int sms = 0;
     P6D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -252,6 +287,24 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
     if (rc) return rc;
     depth_crop_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
         depth, H, W, boxes, B, K, img_size, xyz, center, kcrop, z_mm);
+    P6D_CUDA(cudaGetLastError());
+    return P6D_OK;
+}
+
+int p6d_project_points(const double* points, int N, const double* rotation, int rotation_is_quat,
+                       const double* translation, const double* K, int64_t B, int64_t* uv, int device, void* stream) {
+    if (B < 0 || N < 0 || ((B > 0 && N > 0) && (!points || !rotation || !translation || !K || !uv))) {
+        set_error("p6d_project_points: bad arguments");
+        return P6D_EINVAL;
+    }
+    if (B == 0 || N == 0) return P6D_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    unsigned grid;
+    int rc = grid_for(B * N, device, &grid);
+    if (rc) return rc;
+    project_points_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
+        points, N, rotation, rotation_is_quat, translation, K, B, reinterpret_cast<long long*>(uv));
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;
 }

@@ -185,6 +185,14 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
                                const float* K, int img_size, float* xyz, float* center, float* kcrop,
                                uint16_t* z_mm, int device, void* stream);
 
+/* 3-D -> 2-D projection of N model points for B poses:
+ * utils/visualization.project_points (utils/visualization.py:8-32) in float64 --
+ * rotation [B,4] quaternions (normalised like scipy's Rotation.from_quat) or [B,3,3];
+ * p = R x + t, z clipped to >= 0.001, u = x fx / z + cx, v = y fy / z + cy truncated to
+ * integers; uv [B,N,2] int64. */
+int p6d_project_points(const double* points, int N, const double* rotation, int rotation_is_quat,
+                       const double* translation, const double* K, int64_t B, int64_t* uv, int device, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Measurement helper (no reference counterpart): FP32 issue-rate microbenchmarks that give
  * the roofline its measured denominator.  kind 0 = FFMA only, 1 = packed FFMA2 only,

@@ -302,9 +302,38 @@ def gen_crop():
     save("crop_backproject", **out)
 
 
+def gen_projection():
+    """N4: utils/mesh_utils.load_mesh_corners (PLY -> 1/99 percentile box corners) and
+    utils/visualization.project_points (scipy quaternion -> R, pinhole projection, int
+    truncation) on synthetic inputs."""
+    from utils.mesh_utils import load_mesh_corners
+    from utils.visualization import project_points
+    r = np.random.RandomState(111)
+    d = tempfile.mkdtemp()
+    verts = np.vstack([r.uniform(-80, 80, (400, 3)) * np.array([1.0, 0.6, 0.3]), [[500.0, 0, 0]]])
+    text = "\n".join(["ply", "format ascii 1.0", f"element vertex {len(verts)}", "property float x", "property float y",
+                      "property float z", "element face 2", "property list uchar int vertex_indices", "end_header"] +
+                     [" ".join(f"{x:.5f}" for x in v) for v in verts] + ["3 0 1 2", "3 5 6 7"]) + "\n"
+    open(os.path.join(d, "obj_07.ply"), "w").write(text)
+    corners = load_mesh_corners(d, "07")
+    assert load_mesh_corners(d, "08") is None
+    B = 64
+    pq, pt, gq, gt = W.random_poses(B, 112, rot_sigma=0.3, trans_sigma=0.05)
+    gq64 = gq.astype(np.float64) * r.uniform(0.5, 2.0, (B, 1))        # scipy normalises
+    gt64 = gt.astype(np.float64)
+    gt64[0, 2] = -0.2                                                  # behind the camera -> z clipped to 0.001
+    uv = np.stack([project_points(corners, gq64[b], gt64[b], DEFAULT_K) for b in range(B)])
+    from scipy.spatial.transform import Rotation as R
+    Rm = np.stack([R.from_quat(gq64[b]).as_matrix() for b in range(B)])
+    uv_mat = np.stack([project_points(corners, Rm[b], gt64[b], DEFAULT_K) for b in range(B)])
+    assert np.array_equal(uv, uv_mat)
+    save("projection", ply_text=np.array(text), corners=corners, quat=gq64, trans=gt64, K=DEFAULT_K, uv=uv.astype(np.int64),
+         Rmat=Rm)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_quat(); gen_eval(); gen_forward(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop()
+    gen_quat(); gen_eval(); gen_forward(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_projection()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/gen_golden.py from {REF}\n"
                 f"torch {torch.__version__} cpu_capability {torch.backends.cpu.get_cpu_capability()} "

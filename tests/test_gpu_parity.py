@@ -460,3 +460,15 @@ def test_two_tables_of_different_size_interleaved(pkg, cuda_dev, W, oracle):
         for crit, ref in zip(crits, refs):
             got = crit.eval_poses(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
             assert same_bits(got["add_s"], ref[1]) and same_bits(got["add"], ref[0])
+
+
+def test_project_points_batch(pkg, cuda_dev):
+    """N4 on the GPU: float64 batched projection == the reference's per-pose NumPy result."""
+    import importlib
+    u = importlib.import_module("6d-pose-estimation_b200.utils")
+    g = load_golden("projection")
+    uv = u.project_points_batch(g["corners"], g["quat"], g["trans"], g["K"], device=cuda_dev)
+    assert uv.shape == (64, 8, 2) and uv.dtype == torch.int64
+    assert np.array_equal(uv.cpu().numpy(), g["uv"])
+    uv = u.project_points_batch(g["corners"], g["Rmat"], g["trans"], g["K"], device=cuda_dev)
+    assert np.array_equal(uv.cpu().numpy(), g["uv"])

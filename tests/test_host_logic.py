@@ -149,19 +149,35 @@ def test_dropin_launcher_merges_reference_packages(tmp_path):
     (ref / "models" / "pose_net_rgbd_geometric.py").write_text(
         "class PoseNetRGBDGeometric:\n    def _compute_pinhole_translation(self, d, c, K): return 'reference'\n")
     (ref / "utils" / "__init__.py").write_text("")
-    (ref / "utils" / "mesh_utils.py").write_text("def load_mesh_corners(p): return 'reference'\n")
-    (ref / "utils" / "visualization.py").write_text(
-        "def project_points(*a): return 'reference'\ndef draw_3d_box(*a): pass\ndef draw_axes(*a): pass\n")
+    (ref / "utils" / "extra_tool.py").write_text("def where(): return 'reference'\n")
     (ref / "scripts" / "s.py").write_text(
         "import os, sys\nPROJECT_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))\n"
         "sys.path.insert(0, PROJECT_ROOT)\n"
         "from models.add_loss import ADDLoss\nfrom models.pose_loss import PoseLoss\n"
         "from models.pose_net_rgb import PoseNetRGB\nfrom models.pose_net_rgb_geometric import PoseNetRGBGeometric\n"
         "from utils.mesh_utils import load_mesh_corners\nfrom utils.visualization import project_points\n"
-        "from utils.camera import DEFAULT_K\nfrom utils import draw_3d_box\n"
-        "print(ADDLoss.__module__, getattr(ADDLoss, 'ORIGIN', 'b200'), PoseNetRGB.ORIGIN, load_mesh_corners(0),"
+        "from utils.camera import DEFAULT_K\nfrom utils import draw_3d_box\nfrom utils.extra_tool import where\n"
+        "print(ADDLoss.__module__, getattr(ADDLoss, 'ORIGIN', 'b200'), PoseNetRGB.ORIGIN, where(),"
         " PoseNetRGBGeometric._compute_pinhole_translation.__name__, float(DEFAULT_K[1, 1]))\n")
     launcher = os.path.join(REPO, "6d-pose-estimation_b200", "dropin.py")
     out = subprocess.run([sys.executable, launcher, str(ref), "scripts/s.py"], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0, out.stderr
     assert out.stdout.split() == ["models.add_loss", "b200", "reference", "reference", "<lambda>", "573.57043"]
+
+
+def test_mesh_corners_and_projection_match_reference(pkg, tmp_path):
+    """N4 host helpers against the reference's utils/mesh_utils.py and utils/visualization.py
+    (golden vectors from oracle/gen_golden.py)."""
+    import importlib
+    u = importlib.import_module("6d-pose-estimation_b200.utils")
+    g = load_golden("projection")
+    (tmp_path / "obj_07.ply").write_text(str(g["ply_text"]))
+    assert np.array_equal(u.load_mesh_corners(str(tmp_path), "07"), g["corners"])
+    assert u.load_mesh_corners(str(tmp_path), "08") is None
+    for b in range(len(g["uv"])):
+        assert np.array_equal(u.project_points(g["corners"], g["quat"][b], g["trans"][b], g["K"]), g["uv"][b])
+        assert np.array_equal(u.project_points(g["corners"], g["Rmat"][b], g["trans"][b], g["K"]), g["uv"][b])
+    img = np.zeros((480, 640, 3), np.uint8)
+    uv = np.clip(g["uv"][5], 0, 400)
+    u.draw_3d_box(img, uv); u.draw_axes(img, g["quat"][5], g["trans"][5] + [0, 0, 1.0], g["K"])
+    assert img.any()
