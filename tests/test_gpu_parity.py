@@ -472,3 +472,19 @@ def test_project_points_batch(pkg, cuda_dev):
     assert np.array_equal(uv.cpu().numpy(), g["uv"])
     uv = u.project_points_batch(g["corners"], g["Rmat"], g["trans"], g["K"], device=cuda_dev)
     assert np.array_equal(uv.cpu().numpy(), g["uv"])
+
+
+def test_gpu_invariants_sign_and_identity(pkg, cuda_dev, W):
+    """GPU twin of tests/test_properties.py: q and -q give the same bits; pred == gt gives
+    exact zeros and acceptance; ADD-S <= ADD."""
+    pts, dia = W.sweep_meshes(500)
+    crit = make_crit(pkg, pts, dia, cuda_dev)
+    B = 1300
+    pq, pt, gq, gt = W.random_poses(B, 91, rot_sigma=np.geomspace(1e-3, 0.4, B))
+    obj = np.array(W.LINEMOD_IDS, np.int64)[np.arange(B) % 13]
+    a = crit.eval_poses(*(T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)))
+    b = crit.eval_poses(*(T(x, cuda_dev) for x in (-pq, pt, -gq, gt, obj)))
+    assert same_bits(a["add"], b["add"]) and same_bits(a["add_s"], b["add_s"]) and np.array_equal(a["hit"], b["hit"])
+    assert np.all(a["add_s"] <= a["add"])
+    z = crit.eval_poses(*(T(x, cuda_dev) for x in (gq, gt, gq, gt, obj)))
+    assert not z["add"].any() and not z["add_s"].any() and z["hit"].all()
