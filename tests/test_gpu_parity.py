@@ -255,6 +255,21 @@ def test_add_forward_backward(pkg, cuda_dev, W, oracle):
         scale = np.maximum(np.abs(ref).max(1, keepdims=True), 1e-30)
         assert np.all(np.abs(got.cpu().numpy() - ref) <= 1e-5 * scale)
     assert not torch.any(x.grad[4])
+    # B >= 256 takes the sorted-order path of the forward kernel; value and grads must not care
+    pts3, dia3 = W.sweep_meshes(120)
+    crit3 = make_crit(pkg, pts3, dia3, cuda_dev)
+    B = 600
+    a, b, c, d = W.random_poses(B, 78, rot_sigma=0.05, trans_sigma=0.01)
+    obj = np.array(W.LINEMOD_IDS, np.int64)[np.random.RandomState(79).randint(0, 13, B)]
+    x = T(a, cuda_dev).requires_grad_(True); y = T(b, cuda_dev).requires_grad_(True)
+    loss = crit3(x, y, T(c, cuda_dev), T(d, cuda_dev), T(obj, cuda_dev))
+    loss.backward()
+    ref = oracle.add_forward(oracle.MeshTable(pts3, dia3), a, b, c, d, obj)
+    assert abs(loss.item() - float(ref)) <= 1e-5 * float(ref)
+    rq, rt = oracle.add_backward(oracle.MeshTable(pts3, dia3), a, b, c, d, obj)
+    for got, r in ((x.grad, rq), (y.grad, rt)):
+        scale = np.maximum(np.abs(r).max(1, keepdims=True), 1e-30)
+        assert np.all(np.abs(got.cpu().numpy() - r) <= 1e-5 * scale)
 
 
 # ------------------------------------------------------------------ PoseLoss
