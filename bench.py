@@ -49,6 +49,7 @@ def parse():
                     help="poses timed on the CPU baseline (0 = sized for ~12 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the HBM-bound secondary kernels")
     return ap.parse_args()
 
 
@@ -195,6 +196,61 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def secondary_rooflines(pkg, dev, hbm_peak):
+    """Kernels (a), (c), (d1), (d2) at scaled batches, timed with CUDA events around the bare C-ABI
+    call (no Python wrapper in the timed region).  Algorithmic bytes per row: DESIGN.md section 4."""
+    import torch
+    core, W = pkg.core, pkg.workloads
+    L, st = core.lib(), core.stream_ptr(dev)
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        return best
+
+    out = []
+    n = 1 << 22
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    rnd = lambda *shape: torch.randn(*shape, generator=g, device=dev)
+    pq, gq, pt, gt = rnd(n, 4), rnd(n, 4), rnd(n, 3), rnd(n, 3)
+    o3 = torch.empty(3, device=dev); g1 = torch.empty_like(pq); g2 = torch.empty_like(pt)
+    ws = torch.zeros(64, dtype=torch.uint8, device=dev)
+    t = timed(lambda: core.check(L.p6d_pose_loss_fwd_bwd(pq.data_ptr(), pt.data_ptr(), gq.data_ptr(), gt.data_ptr(), n, 1.0,
+                                                         10.0, 0, o3.data_ptr(), g1.data_ptr(), g2.data_ptr(),
+                                                         ws.data_ptr(), dev.index, st)))
+    out.append(("pose_loss_fwd_bwd (c)", n, 84, t))
+    z, uv = torch.rand(n, device=dev) + 0.4, torch.rand(n, 2, device=dev) * 400
+    K = torch.tensor(pkg.DEFAULT_K, dtype=torch.float32, device=dev).expand(n, 3, 3).contiguous()
+    o = torch.empty(n, 3, device=dev)
+    t = timed(lambda: core.check(L.p6d_pinhole_fwd(z.data_ptr(), uv.data_ptr(), K.data_ptr(), 1, n, o.data_ptr(), dev.index, st)))
+    out.append(("pinhole_fwd (d1)", n, 60, t))
+    m = 1 << 20
+    d8 = torch.rand(m, 8, 8, device=dev) * 1.5
+    uv8 = torch.rand(m, 2, device=dev) * 8
+    o8 = torch.empty(m, 3, device=dev)
+    t = timed(lambda: core.check(L.p6d_depth_backproject(d8.data_ptr(), 8, 8, uv8.data_ptr(), K.data_ptr(), 1, m, 7.0,
+                                                         o8.data_ptr(), dev.index, st)))
+    out.append(("depth_backproject (d2), 8x8 crops", m, 32 + 8 + 36 + 12, t))
+    res = [{"kernel": k, "bound": "hbm", "rows": rows, "bytes_per_row": bpr, "us": round(t * 1e6, 1),
+            "achieved": rows * bpr / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": rows * bpr / t / 1e9 / hbm_peak if hbm_peak else None} for k, rows, bpr, t in out]
+    # (a) ADD only is FP32-issue-bound, not HBM-bound (SURVEY 7.3.4): report poses/s
+    pts = {0: W.sphere_mesh(1000, 0.102, 100)}
+    table = core.MeshTable(pts, {0: 0.102}, pkg.SYMMETRIC_OBJECT_IDS, dev)
+    obj = torch.zeros(m, dtype=torch.int64, device=dev)
+    qa, ta = torch.nn.functional.normalize(rnd(m, 4), dim=1), rnd(m, 3)
+    t = timed(lambda: table.evaluate(qa, ta, qa, ta, obj, want_adds=False), 5)
+    res.append({"kernel": "add_warp_kernel (a), N=1000", "bound": "fp32-issue", "poses": m, "us": round(t * 1e6, 1),
+                "poses_per_s": m / t, "hbm_gbs": m * 73 / t / 1e9})
+    return res
+
+
 # ------------------------------------------------------------------------- GPU arm
 def run_b200(args):
     import torch
@@ -331,6 +387,11 @@ def run_b200(args):
                         "api": "p6d_add_eval_host via MeshTable.evaluate_host (pinned host buffers)"},
                 "gpu_launches": timed_launches, "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
                 "add_01d_acc": 100.0 * hits / valid}
+        if not args.no_secondary and B == POSES_PER_GPU:
+            try:
+                line["secondary_rooflines"] = secondary_rooflines(pkg, dev, peaks.get("hbm_gbs"))
+            except Exception as e:  # never lose the headline line over the side measurements
+                line["secondary_rooflines"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
             n_cpu = args.cpu_sample
             if n_cpu <= 0:
