@@ -236,7 +236,7 @@ def secondary_rooflines(pkg, dev, hbm_peak):
     o8 = torch.empty(m, 3, device=dev)
     t = timed(lambda: core.check(L.p6d_depth_backproject(d8.data_ptr(), 8, 8, uv8.data_ptr(), K.data_ptr(), 1, m, 7.0,
                                                          o8.data_ptr(), dev.index, st)))
-    out.append(("depth_backproject (d2), 8x8 crops", m, 32 + 8 + 36 + 12, t))
+    out.append(("depth_backproject (d2), 8x8 crops (one 32-B sector of each 256-B crop is read)", m, 32 + 8 + 36 + 12, t))
     res = [{"kernel": k, "bound": "hbm", "rows": rows, "bytes_per_row": bpr, "us": round(t * 1e6, 1),
             "achieved": rows * bpr / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": rows * bpr / t / 1e9 / hbm_peak if hbm_peak else None} for k, rows, bpr, t in out]
