@@ -401,14 +401,31 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n_cpu} poses of the same config-2 workload, {dt:.1f} s, "
                                               "oracle/pose_oracle.c (C restatement, bit-exact vs the reference)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract goes to the real stdout; everything else any library
+    prints during the run (e.g. NCCL's version banner) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the duration of the run
     if args.impl == "reference":
         run_reference(args)
     else:
