@@ -193,7 +193,7 @@ def run_reference(args):
                                        "46.5 poses/s on 8 cores for this mesh size, BASELINE.md section 2)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def secondary_rooflines(pkg, dev, hbm_peak):
