@@ -450,6 +450,12 @@ static int adds_max_points_for(int smem_limit) {
 static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_adds, cudaStream_t st,
                        int* launches, int* grid_out = nullptr) {
     if (args.B == 0) return P6D_OK;
+    // poses are claimed through a 32-bit counter that runs up to B + grid
+    if (args.B > static_cast<int64_t>(INT32_MAX) - (1 << 20)) {
+        set_error("p6d_add_eval: B = %lld exceeds the per-launch limit of %d poses; split the batch",
+                  static_cast<long long>(args.B), INT32_MAX - (1 << 20));
+        return P6D_EINVAL;
+    }
     if (!want_adds) {
         int64_t blocks = (args.B + ADD_WARPS - 1) / ADD_WARPS;
         const int64_t cap = static_cast<int64_t>(t->sm_count) * 8;
@@ -498,7 +504,7 @@ static int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_
         }
         a2.scan_reps = reps;
     }
-    a2.work_counter = t->d_counters + (t->counter_idx++ % P6D_NUM_COUNTERS);
+    a2.work_counter = t->d_counters + (__atomic_fetch_add(&t->counter_idx, 1u, __ATOMIC_RELAXED) % P6D_NUM_COUNTERS);
     P6D_CUDA(cudaMemsetAsync(a2.work_counter, 0, sizeof(int), st));
     int nmax = t->max_count;
     void* kargs[] = {&a2, &nmax};

@@ -17,7 +17,12 @@
  *     contiguous, quaternions scalar-last [x,y,z,w], translations in metres, K row-major
  *     3x3; the caller owns every buffer;
  *   - there is no CPU fallback: without a CUDA device every compute entry fails with
- *     P6D_ECUDA.
+ *     P6D_ECUDA;
+ *   - threading: the table-less entries and p6d_add_eval / p6d_add_backward may be called
+ *     from several host threads at once (launches on different streams of one table use
+ *     separate scheduler counters, up to 256 in flight); the *_host entries and
+ *     create/destroy own the table's staging buffers and must not run concurrently on
+ *     the same table.  One launch takes at most 2^31 - 2^20 poses.
  */
 #ifndef P6D_H_
 #define P6D_H_

@@ -216,6 +216,20 @@ def test_mesh_too_large_is_a_loud_error(pkg, cuda_dev, W):
         crit.eval_metrics(pq, pt[:1], gq, gt, torch.zeros(2, dtype=torch.long, device=cuda_dev))
 
 
+def test_batch_beyond_the_launch_limit_is_refused(pkg, cuda_dev, W):
+    # the pose scheduler claims work through a 32-bit counter: the C ABI refuses larger launches
+    crit = make_crit(pkg, {0: W.sphere_mesh(64, 0.1, 1)}, {0: 0.1}, cuda_dev)
+    table = crit._mesh_table(cuda_dev)
+    buf = torch.zeros(64, dtype=torch.float32, device=cuda_dev)
+    obj = torch.zeros(8, dtype=torch.long, device=cuda_dev)
+    out = torch.zeros(64, dtype=torch.uint8, device=cuda_dev)
+    L, ptr = pkg.core.lib(), pkg.core.ptr
+    rc = L.p6d_add_eval(table.handle, ptr(buf), ptr(buf), ptr(buf), ptr(buf), ptr(obj), None, 2 ** 31,
+                        ptr(buf), ptr(buf), ptr(out), ptr(out), None, None)
+    assert rc == pkg.core.P6D_EINVAL and b"split the batch" in L.p6d_last_error()
+    torch.cuda.synchronize(cuda_dev)
+
+
 def test_add_forward_value(pkg, cuda_dev):
     g = load_golden("add_forward")
     pts, dia = golden_meshes(g)

@@ -1,0 +1,139 @@
+// exp_block.cu -- dev experiment: keep the minima of the ADD-S scan out of the packed-op stream.
+// ptxas interleaves FMNMX with the packed FP32 ops of the same warp (it models that pair as dual issue);
+// measured (tools/exp_order.cu) that placement is the slowest one, while a run of FMNMX from one warp
+// overlaps with the packed ops of the other warps.  Here an opaque, never-taken branch splits the loop
+// body into a math block and a min block, which ptxas schedules separately.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -lineinfo -o exp_block exp_block.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <vector>
+#define SUB2(r, a, b) asm volatile("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%2}; mov.b64 rb, {%3,%4}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}" : "=f"(r.x), "=f"(r.y) : "f"(a), "f"(b.x), "f"(b.y))
+#define MUL2(r, a) asm volatile("{.reg .b64 ra, rc; mov.b64 ra, {%2,%3}; mul.rn.f32x2 rc, ra, ra; mov.b64 {%0,%1}, rc;}" : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y))
+#define FMA2(r, a) asm volatile("{.reg .b64 ra, rc; mov.b64 ra, {%2,%3}; mov.b64 rc, {%0,%1}; fma.rn.f32x2 rc, ra, ra, rc; mov.b64 {%0,%1}, rc;}" : "+f"(r.x), "+f"(r.y) : "f"(a.x), "f"(a.y))
+#define MIN3(m, s) asm volatile("min.NaN.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(s.x), "f"(s.y))
+#define MIN2(m, v) asm volatile("min.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(v))
+
+// a branch ptxas cannot remove or predicate: the cold side is a loop with stores
+#define SPLIT(flag, out) do { if (__builtin_expect(flag != 0, 0)) { for (int q_ = 0; q_ < flag; ++q_) (out)[threadIdx.x + 32 * q_] = (float)q_; } } while (0)
+
+// MODE 0: math block | split | 2-source minima (2K accumulators)
+// MODE 1: math block | split | FMNMX3 (K accumulators)
+// MODE 2: loads | split | minima of the previous trip (2-source) | split | math   (minima fill the LDS latency)
+// MODE 3: like 2 with FMNMX3
+// MODE 4: no split, 2-source minima in source order (= exp_order ORDER 5)
+template <int T, int K, int MINB, int MODE>
+__global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__ g, int nquads, int reps, float* out, int flag) {
+    extern __shared__ float4 sm[];
+    for (int i = threadIdx.x; i < 3 * nquads; i += T) sm[i] = reinterpret_cast<const float4*>(g)[i];
+    __syncthreads();
+    float px[K], py[K], pz[K], m[K], m2[K], m3[K], m4[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        m2[k] = m3[k] = m4[k] = 3.0e38f;
+        px[k] = g[(threadIdx.x * K + k) % (4 * nquads)];
+        py[k] = g[(threadIdx.x * K + k + 7) % (4 * nquads)] * 0.5f;
+        pz[k] = g[(threadIdx.x * K + k + 13) % (4 * nquads)] * 0.25f;
+        m[k] = 3.0e38f;
+    }
+    for (int r = 0; r < reps; ++r) {
+        float2 pa[K], pb[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) pa[k] = pb[k] = make_float2(3.0e38f, 3.0e38f);
+        const float4* p = sm;
+        const float4* const pe = sm + 3 * nquads;
+#pragma unroll 1
+        for (; p < pe; p += 3) {
+            const float4 X = p[0], Y = p[1], Z = p[2];
+            if (MODE == 2 || MODE == 3) {
+                SPLIT(flag, out);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (MODE == 2) { MIN2(m[k], pa[k].x); MIN2(m2[k], pa[k].y); MIN2(m3[k], pb[k].x); MIN2(m4[k], pb[k].y); }
+                    else { MIN3(m[k], pa[k]); MIN3(m[k], pb[k]); }
+                }
+                SPLIT(flag, out + 7);
+            }
+            float2 sa[K], sb[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                float2 dx, dy, dz;
+                SUB2(dx, px[k], make_float2(X.x, X.y)); SUB2(dy, py[k], make_float2(Y.x, Y.y)); SUB2(dz, pz[k], make_float2(Z.x, Z.y));
+                MUL2(sa[k], dx); FMA2(sa[k], dy); FMA2(sa[k], dz);
+                SUB2(dx, px[k], make_float2(X.z, X.w)); SUB2(dy, py[k], make_float2(Y.z, Y.w)); SUB2(dz, pz[k], make_float2(Z.z, Z.w));
+                MUL2(sb[k], dx); FMA2(sb[k], dy); FMA2(sb[k], dz);
+                if (MODE == 4) { MIN2(m[k], sa[k].x); MIN2(m2[k], sa[k].y); MIN2(m3[k], sb[k].x); MIN2(m4[k], sb[k].y); }
+            }
+            if (MODE == 0 || MODE == 1) {
+                SPLIT(flag, out);
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (MODE == 0) { MIN2(m[k], sa[k].x); MIN2(m2[k], sa[k].y); MIN2(m3[k], sb[k].x); MIN2(m4[k], sb[k].y); }
+                    else { MIN3(m[k], sa[k]); MIN3(m[k], sb[k]); }
+                }
+            }
+            if (MODE == 2 || MODE == 3) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) { pa[k] = sa[k]; pb[k] = sb[k]; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) { MIN3(m[k], pa[k]); MIN3(m[k], pb[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) { MIN2(m[k], m2[k]); MIN2(m3[k], m4[k]); MIN2(m[k], m3[k]); }
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s += m[k];
+    if (s == 123.456f) out[0] = s;
+}
+
+template <int T, int K, int MINB, int MODE>
+void run(const char* name, const float* d_g, float* d_out, int nquads, int reps, int sms) {
+    auto kern = scan_kernel<T, K, MINB, MODE>;
+    size_t smem = (size_t)3 * nquads * sizeof(float4);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem);
+    int grid = sms * per_sm;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    kern<<<grid, T, smem>>>(d_g, nquads, reps / 4 + 1, d_out, 0);
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int it = 0; it < 3; ++it) {
+        cudaEventRecord(e0); kern<<<grid, T, smem>>>(d_g, nquads, reps, d_out, 0); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    double pairs = (double)grid * T * K * (double)nquads * 4.0 * reps;
+    double tf = pairs * 8.0 / (best * 1e-3) / 1e12;
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    printf("%-34s T=%4d K=%d ctas/sm=%d regs=%3d %8.3f ms %6.2f TFLOP/s %5.1f%% of 74.45 %s\n", name, T, K, per_sm, fa.numRegs,
+           best, tf, tf / 74.45 * 100.0, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+int main() {
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int nquads = 512;
+    std::vector<float> h(12 * nquads); srand(1);
+    for (auto& v : h) v = (rand() % 2000) * 1e-4f;
+    float *d_g, *d_out; cudaMalloc(&d_g, h.size() * sizeof(float)); cudaMalloc(&d_out, 1 << 20);
+    cudaMemcpy(d_g, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+    const int reps = 64;
+    run<512, 4, 2, 4>("K4 T512 no split 2xFMNMX", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 0>("K4 T512 math|min2", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 1>("K4 T512 math|min3", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 2>("K4 T512 lds|min2(prev)|math", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 3>("K4 T512 lds|min3(prev)|math", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 4>("K8 T256 no split 2xFMNMX", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 0>("K8 T256 math|min2", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 1>("K8 T256 math|min3", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 2>("K8 T256 lds|min2(prev)|math", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 3>("K8 T256 lds|min3(prev)|math", d_g, d_out, nquads, reps, sms);
+    run<256, 4, 4, 0>("K4 T256x4 math|min2", d_g, d_out, nquads, reps, sms);
+    run<256, 4, 4, 2>("K4 T256x4 lds|min2(prev)|math", d_g, d_out, nquads, reps, sms);
+    run<128, 4, 8, 0>("K4 T128x8 math|min2", d_g, d_out, nquads, reps, sms);
+    run<1024, 4, 1, 0>("K4 T1024 math|min2", d_g, d_out, nquads, reps, sms);
+    run<1024, 4, 1, 2>("K4 T1024 lds|min2(prev)|math", d_g, d_out, nquads, reps, sms);
+    return 0;
+}
