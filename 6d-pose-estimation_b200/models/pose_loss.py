@@ -54,23 +54,25 @@ class _FusedPoseLoss(torch.autograd.Function):
         need_q = ctx.needs_input_grad[0]
         need_t = ctx.needs_input_grad[1]
         out = torch.empty(3, dtype=torch.float32, device=dev)
-        gq_out = torch.empty_like(pq) if need_q else None
-        gt_out = torch.empty_like(pt) if need_t else None
+        # both gradients live in one buffer so that backward scales them with one launch
+        flat = torch.empty(7 * B, dtype=torch.float32, device=dev) if (need_q or need_t) else None
+        gq_out = flat[:4 * B] if need_q else None
+        gt_out = flat[4 * B:] if need_t else None
         core.check(core.lib().p6d_pose_loss_fwd_bwd(
             core.ptr(pq), core.ptr(pt), core.ptr(gq), core.ptr(gt), B, float(rot_weight), float(trans_weight),
             int(mode), core.ptr(out), core.ptr(gq_out), core.ptr(gt_out), core.ptr(_workspace(dev)),
             dev.index, core.stream_ptr(dev)))
-        ctx.grads = (gq_out, gt_out)
-        ctx.meta = (pred_rot.shape, pred_trans.shape, pred_rot.dtype, pred_trans.dtype, pick)
-        return out[pick].clone()
+        ctx.flat = flat
+        ctx.meta = (pred_rot.shape, pred_trans.shape, pred_rot.dtype, pred_trans.dtype, need_q, need_t, B)
+        return out[pick]
 
     @staticmethod
     def backward(ctx, grad_out):
-        gq, gt = ctx.grads
-        rs, ts, rd, td, pick = ctx.meta
+        rs, ts, rd, td, need_q, need_t, B = ctx.meta
         # pick 0: d loss; pick 1: d rot_term (the kernel ran with rot_weight 1, trans_weight 0)
-        dq = (gq * grad_out).reshape(rs).to(rd) if gq is not None else None
-        dt = (gt * grad_out).reshape(ts).to(td) if gt is not None else None
+        scaled = ctx.flat * grad_out
+        dq = scaled[:4 * B].reshape(rs).to(rd) if need_q else None
+        dt = scaled[4 * B:].reshape(ts).to(td) if need_t else None
         return dq, dt, None, None, None, None, None, None
 
 
@@ -99,23 +101,25 @@ class _FusedGeometricPoseLoss(torch.autograd.Function):
             raise ValueError("camera_matrix must be [3,3] or [B,3,3]")
         out = torch.empty(3, dtype=torch.float32, device=dev)
         trans = torch.empty(B, 3, dtype=torch.float32, device=dev)
-        gq_out = torch.empty_like(pq) if ctx.needs_input_grad[0] else None
-        gz_out = torch.empty(B, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        need_q, need_z = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        flat = torch.empty(5 * B, dtype=torch.float32, device=dev) if (need_q or need_z) else None
+        gq_out = flat[:4 * B] if need_q else None
+        gz_out = flat[4 * B:] if need_z else None
         core.check(core.lib().p6d_pose_loss_pinhole_fwd_bwd(
             core.ptr(pq), core.ptr(z), core.ptr(uv), core.ptr(K), kb, core.ptr(gq), core.ptr(gt), B,
             float(rot_weight), float(trans_weight), int(mode), core.ptr(out), core.ptr(gq_out), core.ptr(gz_out),
             core.ptr(trans), core.ptr(_workspace(dev)), dev.index, core.stream_ptr(dev)))
-        ctx.grads = (gq_out, gz_out)
-        ctx.meta = (pred_rot.shape, z_pred.shape, pred_rot.dtype, z_pred.dtype)
+        ctx.flat = flat
+        ctx.meta = (pred_rot.shape, z_pred.shape, pred_rot.dtype, z_pred.dtype, need_q, need_z, B)
         ctx.mark_non_differentiable(trans)
-        return out[0].clone(), trans
+        return out[0], trans
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_trans):
-        gq, gz = ctx.grads
-        rs, zs, rd, zd = ctx.meta
-        dq = (gq * grad_loss).reshape(rs).to(rd) if gq is not None else None
-        dz = (gz * grad_loss).reshape(zs).to(zd) if gz is not None else None
+        rs, zs, rd, zd, need_q, need_z, B = ctx.meta
+        scaled = ctx.flat * grad_loss
+        dq = scaled[:4 * B].reshape(rs).to(rd) if need_q else None
+        dz = scaled[4 * B:].reshape(zs).to(zd) if need_z else None
         return dq, dz, None, None, None, None, None, None, None
 
 

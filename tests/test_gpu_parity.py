@@ -491,6 +491,45 @@ def test_two_tables_of_different_size_interleaved(pkg, cuda_dev, W, oracle):
             assert same_bits(got["add_s"], ref[1]) and same_bits(got["add"], ref[0])
 
 
+def test_concurrent_launches_on_one_table_from_two_threads(pkg, cuda_dev, W, oracle):
+    """include/p6d.h: p6d_add_eval may be called from several host threads on one table; each
+    launch takes its own scheduler counter, so launches overlapping on two streams keep their bits."""
+    import threading
+    mesh = ({9: W.sphere_mesh(700, 0.12, 5)}, {9: 0.12})
+    crit = make_crit(pkg, *mesh, cuda_dev)
+    table = crit._mesh_table(cuda_dev)
+    batches = []
+    for seed in (11, 12):
+        pq, pt, gq, gt = W.random_poses(3000, seed)
+        obj = np.full(3000, 9, np.int64)
+        ref = oracle.add_eval(oracle.MeshTable(*mesh), pq[:64], pt[:64], gq[:64], gt[:64], obj[:64], n_threads=4)
+        batches.append(([T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)], ref))
+    torch.cuda.synchronize(cuda_dev)
+    results, errors = [None, None], []
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream(device=cuda_dev)
+            with torch.cuda.stream(stream):
+                outs = [table.evaluate(*batches[i][0]) for _ in range(8)]
+            stream.synchronize()
+            results[i] = [(o[0].cpu().numpy(), o[1].cpu().numpy(), o[2].cpu().numpy()) for o in outs]
+        except Exception as e:  # surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(2):
+        ref = batches[i][1]
+        first = results[i][0]
+        assert same_bits(first[0][:64], ref[0]) and same_bits(first[1][:64], ref[1])
+        assert np.array_equal(first[2][:64], ref[2])
+        for other in results[i][1:]:
+            assert all(np.array_equal(a, b) for a, b in zip(first, other))
+
+
 def test_project_points_batch(pkg, cuda_dev):
     """N4 on the GPU: float64 batched projection == the reference's per-pose NumPy result."""
     import importlib
