@@ -27,7 +27,7 @@ P6D_OK, P6D_EINVAL, P6D_ECUDA, P6D_ENOMEM, P6D_ETOOBIG = 0, -1, -2, -3, -4
 
 EXPORTS = (
     "p6d_version", "p6d_last_error", "p6d_device_info", "p6d_mesh_table_create",
-    "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_add_eval", "p6d_add_eval_host",
+    "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_adds_schedule", "p6d_add_eval", "p6d_add_eval_host",
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
     "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject", "p6d_fp32_microbench",
     "p6d_adds_timeline", "p6d_add_backward", "p6d_depth_crop_backproject", "p6d_pose_loss_pinhole_fwd_bwd",

@@ -191,9 +191,63 @@ __device__ __forceinline__ void scan_quads(const float4* __restrict__ p, int ste
     }
 }
 
+// two pairs of one tile without the minimum: the squared distances go to `s`
+__device__ __forceinline__ float2 pair_sq(float px, float py, float pz, float2 gx, float2 gy, float2 gz) {
+    const float2 dx = sub2(make_float2(px, px), gx);
+    const float2 dy = sub2(make_float2(py, py), gy);
+    const float2 dz = sub2(make_float2(pz, pz), gz);
+    float2 s = mul2(dx, dx);
+    s = fma2(dy, dy, s);
+    return fma2(dz, dz, s);
+}
+
+// Software-pipelined form of the unit-stride scan (one quad per trip): the minima of trip t are
+// taken during trip t+1, so their operands are ready from the top of the loop body and their
+// position between the packed ops is free.  ptxas parks them at the top; the post-link pass
+// tools/sass_sched.py (run by the Makefile) spreads them behind FADD2s, which is measurably the
+// cheapest place on B200 (NOTES.md).  The arithmetic per pair and the set of values that enter each
+// minimum are the same as in scan_quads, so every bit of the result is too.
+template <int K>
+__device__ __forceinline__ void scan_deferred(const float4* __restrict__ p, const float4* __restrict__ pend,
+                                              const float (&px)[K], const float (&py)[K],
+                                              const float (&pz)[K], float (&m)[K]) {
+    float2 sa[K], sb[K];
+    float m2[K];
+    const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        sa[k] = make_float2(inf, inf);
+        sb[k] = make_float2(inf, inf);
+        m2[k] = inf;
+    }
+#pragma unroll 1
+    for (; p < pend; p += 3) {
+        const float4 X = p[0], Y = p[1], Z = p[2];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            m[k] = min3_nan(m[k], sa[k].x, sa[k].y);
+            m2[k] = min3_nan(m2[k], sb[k].x, sb[k].y);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            sa[k] = pair_sq(px[k], py[k], pz[k], make_float2(X.x, X.y), make_float2(Y.x, Y.y), make_float2(Z.x, Z.y));
+            sb[k] = pair_sq(px[k], py[k], pz[k], make_float2(X.z, X.w), make_float2(Y.z, Y.w), make_float2(Z.z, Z.w));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        m[k] = min3_nan(m[k], sa[k].x, sa[k].y);
+        m2[k] = min3_nan(m2[k], sb[k].x, sb[k].y);
+        m[k] = min_nan(m[k], m2[k]);
+    }
+}
+
 // T threads per CTA, K pred points per thread, MINB CTAs per SM, U gt quads per loop trip
-template <int T, int K, int MINB, int U>
+// (U == 0: one quad per trip with software-pipelined minima, see scan_deferred)
+template <int T, int K, int MINB, int U_>
 __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax) {
+    constexpr bool DEFER = U_ == 0;
+    constexpr int U = DEFER ? 1 : U_;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int npmax = round_up(nmax, 4);
     const int ngmax = adds_ngmax(nmax);
@@ -333,8 +387,12 @@ __global__ void __launch_bounds__(T, MINB) adds_cta_kernel(EvalArgs a, int nmax)
                 // large meshes: unit stride, one pointer, immediate offsets
                 const float4* p = gq4;
                 const float4* const pend = gq4 + 3 * nquads;
+                if (DEFER) {
+                    scan_deferred<K>(p, pend, px, py, pz, m);
+                } else {
 #pragma unroll 1
-                for (; p < pend; p += 3 * U) scan_quads<K, U>(p, 3, px, py, pz, m);
+                    for (; p < pend; p += 3 * U) scan_quads<K, U>(p, 3, px, py, pz, m);
+                }
             } else {
                 const int step = 3 * S;
 #pragma unroll 1
@@ -401,8 +459,21 @@ static const AddsVariant g_adds_variants[] = {
     // flight and hide each other's per-pose latencies (scheduler atomic, parameter loads, barriers)
     {"T256_K4_B4_U2", 256, (const void*)adds_cta_kernel<256, 4, 4, 2>},
     {"T128_K4_B8_U2", 128, (const void*)adds_cta_kernel<128, 4, 8, 2>},
+    // 7, 8: software-pipelined minima (U = 0), re-scheduled after linking by tools/sass_sched.py
+    {"T512_K4_B2_D", 512, (const void*)adds_cta_kernel<512, 4, 2, 0>},
+    {"T256_K8_B2_D", 256, (const void*)adds_cta_kernel<256, 8, 2, 0>},
 };
 constexpr int N_ADDS_VARIANTS = sizeof(g_adds_variants) / sizeof(g_adds_variants[0]);
+
+}  // namespace p6d
+// State of the post-link scheduling pass (sass_sched.py, run by the Makefile): the pass rewrites
+// "ptxas" to "tuned" in the built library after it has re-laid the scan loop of variant 8, so the
+// default below only selects that variant when the pass really ran.
+extern "C" __attribute__((visibility("default"), used)) volatile const char p6d_sched_state[24] =
+    "P6D-SCHED-STATE:ptxas";
+namespace p6d {
+
+static bool scan_loop_is_rescheduled() { return p6d_sched_state[16] == 't'; }
 
 // Variant for a table whose largest mesh has nmax points; P6D_ADDS_VARIANT overrides (experiments).
 static int adds_variant(int nmax) {
@@ -415,7 +486,9 @@ static int adds_variant(int nmax) {
     if (forced >= 0) return forced;
     if (nmax <= 512) return 6;
     if (nmax <= 1024) return 5;
-    return 0;
+    // software-pipelined minima pay off only with the re-laid loop (B200, N = 2048: 1.333 M poses/s
+    // re-laid, 1.257 M as ptxas schedules the same source, 1.276 M for variant 0)
+    return scan_loop_is_rescheduled() ? 8 : 0;
 }
 
 // ------------------------------------------------------------------ quat -> R (API parity)
@@ -539,6 +612,8 @@ int p6d_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int
     }
     return P6D_OK;
 }
+
+int p6d_adds_schedule(void) { return scan_loop_is_rescheduled() ? 1 : 0; }
 
 int p6d_adds_max_points(int device, int* max_points) {
     if (!max_points) { set_error("max_points is NULL"); return P6D_EINVAL; }

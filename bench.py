@@ -362,7 +362,10 @@ def run_b200(args):
         sm_max = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
         nominal = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
         tr = profiled_traffic() if B == POSES_PER_GPU else None
+        relaid = bool(core.lib().p6d_adds_schedule())
         roof = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s",
+                "kernel": ("adds_cta_kernel<256,8,2,deferred minima>, scan loop re-laid after linking by "
+                           "csrc/sass_sched.py") if relaid else "adds_cta_kernel<512,4,2,2> (ptxas schedule)",
                 "frac": achieved / nominal, "traffic": tr["bytes"] if tr else None,
                 "traffic_source": tr["source"] if tr else None,
                 "algorithmic_bytes_per_launch": B * BYTES_PER_POSE,

@@ -72,6 +72,10 @@ int p6d_mesh_table_destroy(p6d_mesh_table* table);
 /* Largest mesh (points) the ADD-S kernel accepts on this device. */
 int p6d_adds_max_points(int device, int* max_points);
 
+/* 1 if the build's post-link pass (csrc/sass_sched.py) re-laid the ADD-S scan loop, 0 if the
+ * library runs ptxas' own schedule (same results, about 4 % slower at 2,048 points). */
+int p6d_adds_schedule(void);
+
 /* ---------------------------------------------------------------------------------------
  * Per-pose evaluation = the loop body of ADDLoss.eval_metrics (models/add_loss.py:168-195)
  * for B poses in one launch.

@@ -7,6 +7,8 @@ distances and loss within 1e-5 relative.  Distances are in fact checked for bit 
 (the kernels reproduce the reference's float32 rounding and summation order); the
 transcendental loss is checked at 1e-5.
 """
+import json
+import os
 import tempfile
 
 import numpy as np
@@ -528,6 +530,18 @@ def test_concurrent_launches_on_one_table_from_two_threads(pkg, cuda_dev, W, ora
         assert np.array_equal(first[2][:64], ref[2])
         for other in results[i][1:]:
             assert all(np.array_equal(a, b) for a, b in zip(first, other))
+
+
+def test_every_large_mesh_kernel_variant_gives_the_same_bits(pkg, cuda_dev):
+    """Variant 8 (software-pipelined minima, scan loop re-laid after linking) is the default for
+    large meshes; variants 0 and 7 are ptxas-scheduled.  All must produce identical outputs."""
+    import subprocess, sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "variants.py")
+    r = subprocess.run([sys.executable, tool, "0,7,8,auto", "4096", "1500"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    rows = [json.loads(l.split(" ", 1)[1]) for l in r.stdout.strip().splitlines()]
+    assert len(rows) == 4 and len({x["hash"] for x in rows}) == 1, r.stdout
+    assert pkg.core.lib().p6d_adds_schedule() == 1
 
 
 def test_project_points_batch(pkg, cuda_dev):

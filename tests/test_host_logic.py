@@ -25,6 +25,27 @@ def test_library_exports_every_declared_symbol(pkg):
     assert pkg.core.lib().p6d_version() == 1
 
 
+def test_post_link_scheduling_pass_ran_and_its_checks_hold(pkg):
+    """The build re-lays the scan loop of the large-mesh ADD-S kernel (csrc/sass_sched.py).  No GPU
+    is needed to check the pass: it must have marked the library, and planning the same pass on a
+    kernel it has not touched (variant 7, same source shape) must get through every safety rule."""
+    import subprocess, sys
+    from pathlib import Path
+    csrc = Path(pkg.core.SO_PATH).parent
+    assert pkg.core.lib().p6d_adds_schedule() == 1, "libp6d.so runs the ptxas schedule: rebuild (make -C csrc)"
+    r = subprocess.run([sys.executable, str(csrc / "sass_sched.py"), pkg.core.SO_PATH,
+                        "adds_cta_kernelILi512ELi4ELi2ELi0E", "spaced=FADD2:2", "--loop=uniform",
+                        "--packed-stall=1", "--yield=period8,0"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "8 movable minima" in r.stdout and "48 packed" in r.stdout
+    # a plan that would break a dependency is refused: the identity policy on the ALREADY re-laid
+    # kernel is fine, marking twice is not
+    r2 = subprocess.run([sys.executable, str(csrc / "sass_sched.py"), pkg.core.SO_PATH,
+                         "adds_cta_kernelILi256ELi8ELi2ELi0E", "identity", "--loop=uniform", "--mark",
+                         "--out=/dev/null"], capture_output=True, text=True)
+    assert r2.returncode != 0 and "marker" in (r2.stdout + r2.stderr)
+
+
 def test_no_cpu_fallback(pkg):
     crit = pkg.ADDLoss(tempfile.mkdtemp(), "cpu")
     crit.points[0] = torch.zeros(16, 3)

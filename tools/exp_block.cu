@@ -22,6 +22,9 @@
 // MODE 2: loads | split | minima of the previous trip (2-source) | split | math   (minima fill the LDS latency)
 // MODE 3: like 2 with FMNMX3
 // MODE 4: no split, 2-source minima in source order (= exp_order ORDER 5)
+// MODE 5: no split, 2-source minima of the PREVIOUS trip (software pipelined: their inputs are ready from
+//         the top of the body, so a post-pass (tools/sass_sched.py) is free to place them anywhere)
+// MODE 6: like 5 with FMNMX3
 template <int T, int K, int MINB, int MODE>
 __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__ g, int nquads, int reps, float* out, int flag) {
     extern __shared__ float4 sm[];
@@ -54,6 +57,13 @@ __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__
                 }
                 SPLIT(flag, out + 7);
             }
+            if (MODE == 5 || MODE == 6) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    if (MODE == 5) { MIN2(m[k], pa[k].x); MIN2(m2[k], pa[k].y); MIN2(m3[k], pb[k].x); MIN2(m4[k], pb[k].y); }
+                    else { MIN3(m[k], pa[k]); MIN3(m2[k], pb[k]); }
+                }
+            }
             float2 sa[K], sb[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
@@ -72,7 +82,7 @@ __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__
                     else { MIN3(m[k], sa[k]); MIN3(m[k], sb[k]); }
                 }
             }
-            if (MODE == 2 || MODE == 3) {
+            if (MODE == 2 || MODE == 3 || MODE == 5 || MODE == 6) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) { pa[k] = sa[k]; pb[k] = sb[k]; }
             }
@@ -86,6 +96,8 @@ __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__
 #pragma unroll
     for (int k = 0; k < K; ++k) s += m[k];
     if (s == 123.456f) out[0] = s;
+    // checksum for tools/exp_cubin.cu (patched schedules must reproduce it bit for bit)
+    if (flag < 0) out[(size_t)blockIdx.x * T + threadIdx.x] = s;
 }
 
 template <int T, int K, int MINB, int MODE>
@@ -135,5 +147,8 @@ int main() {
     run<128, 4, 8, 0>("K4 T128x8 math|min2", d_g, d_out, nquads, reps, sms);
     run<1024, 4, 1, 0>("K4 T1024 math|min2", d_g, d_out, nquads, reps, sms);
     run<1024, 4, 1, 2>("K4 T1024 lds|min2(prev)|math", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 5>("K8 T256 deferred min2, no split", d_g, d_out, nquads, reps, sms);
+    run<256, 8, 2, 6>("K8 T256 deferred min3, no split", d_g, d_out, nquads, reps, sms);
+    run<512, 4, 2, 6>("K4 T512 deferred min3, no split", d_g, d_out, nquads, reps, sms);
     return 0;
 }
