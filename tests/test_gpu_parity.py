@@ -542,6 +542,12 @@ def test_every_large_mesh_kernel_variant_gives_the_same_bits(pkg, cuda_dev):
     rows = [json.loads(l.split(" ", 1)[1]) for l in r.stdout.strip().splitlines()]
     assert len(rows) == 4 and len({x["hash"] for x in rows}) == 1, r.stdout
     assert pkg.core.lib().p6d_adds_schedule() == 1
+    # small-mesh shapes: 5 / 6 (ptxas) against their re-laid counterparts 9 / 10
+    for variants, n in (("5,9,auto", "900"), ("6,10,auto", "500")):
+        r = subprocess.run([sys.executable, tool, variants, "4096", n], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-500:]
+        rows = [json.loads(l.split(" ", 1)[1]) for l in r.stdout.strip().splitlines()]
+        assert len(rows) == 3 and len({x["hash"] for x in rows}) == 1, r.stdout
 
 
 def test_project_points_batch(pkg, cuda_dev):
