@@ -29,7 +29,9 @@ Safety rules (checked; the patch is refused when one fails):
 The GPU parity tests (bit-exact against the oracle) run on the patched library.
 
 Usage: sass_sched.py FILE KERNEL-SUBSTRING POLICY [OUT | --out=OUT] [--loop=uniform|0xADDR]
-                     [--packed-stall=1] [--yield=periodP,PHASE|0|1] [--mark] [--show]
+                     [--packed-stall=1] [--yield=periodP,PHASE|mask0110..|0|1] [--order=i,j,..] [--mark] [--show]
+       sass_sched.py FILE --plan=PLAN.json [--out=OUT] [--loop=uniform] [--mark]     (order + yield mask from
+                                                                                   tools/sched_search.py)
 POLICY: identity | cluster_end | spaced=FADD2:2[,FMUL2:1][/next=FADD2+FMUL2]
 """
 import re
@@ -390,11 +392,19 @@ def patch_file(path, out, kernel_instrs, body, blob, mark=False):
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     opts = dict(a[2:].split("=", 1) if "=" in a else (a[2:], "1") for a in sys.argv[1:] if a.startswith("--"))
+    if "plan" in opts:      # a schedule found by tools/sched_search.py: explicit order + yield mask
+        import json
+        plan = json.load(open(opts["plan"]))
+        opts.setdefault("order", ",".join(str(k) for k in plan["order"]))
+        opts.setdefault("yield", "mask" + plan["yield_mask"])
+        opts.setdefault("packed-stall", str(plan.get("packed_stall", 1)))
+        if len(args) == 1:
+            args += [plan["kernel"], "plan"]
     path, kernel, policy = args[:3]
     out = opts.get("out") or (args[3] if len(args) > 3 else None)
     kernel_instrs = load(path, kernel)
     body = pick_loop(kernel_instrs, opts.get("loop"))
-    order = make_order(body, policy)
+    order = [int(x) for x in opts["order"].split(",")] if "order" in opts else make_order(body, policy)
     check_order(body, order)
     n = len(order)
     if policy == "identity" and "packed-stall" not in opts:
@@ -406,6 +416,10 @@ def main():
     y = opts.get("yield")
     if y in ("0", "1"):
         yields = [int(y)] * n
+    elif y and y.startswith("mask"):
+        yields = [int(c) for c in y[4:]]
+        if len(yields) != n:
+            raise SystemExit("sass_sched: yield mask length does not match the loop")
     elif y and y.startswith("period"):
         per, ph = (int(x) for x in y[6:].split(","))
         yields = [0 if (q % per) == ph else 1 for q in range(n)]
