@@ -81,24 +81,31 @@ best_t, h = evaluate(order, yields)
 assert h == h0
 print(f"ptxas schedule {t_ptxas:.3f} ms; start recipe {best_t:.3f} ms", flush=True)
 t_end = time.time() + budget
-rng = random.Random(1)
+rng = random.Random(int(os.environ.get('SEARCH_SEED', '1')))
 evals, accepted = 0, 0
-while time.time() < t_end:
-    kind = rng.random()
-    cand_o, cand_y = list(order), list(yields)
-    if kind < 0.5:
+def mutate(cand_o, cand_y):
+    if rng.random() < 0.5:
         p = rng.randrange(n - 1)
         cand_y[p] ^= 1
-        what = f"yield[{p}]"
-    else:
-        mins = [p for p, k in enumerate(cand_o) if S.movable(body[k])]
-        p = rng.choice(mins)
-        q = p + rng.choice((-1, 1))
-        if q < 0 or q >= n - 1:
-            continue
-        cand_o[p], cand_o[q] = cand_o[q], cand_o[p]
-        cand_y[p], cand_y[q] = cand_y[q], cand_y[p]
-        what = f"min {p}->{q}"
+        return f"yield[{p}]"
+    mins = [p for p, k in enumerate(cand_o) if S.movable(body[k])]
+    p = rng.choice(mins)
+    q = p + rng.choice((-1, 1))
+    if q < 0 or q >= n - 1:
+        return None
+    cand_o[p], cand_o[q] = cand_o[q], cand_o[p]
+    cand_y[p], cand_y[q] = cand_y[q], cand_y[p]
+    return f"min {p}->{q}"
+
+
+while time.time() < t_end:
+    cand_o, cand_y = list(order), list(yields)
+    # single moves have converged once; 40 % of the candidates now combine two or three changes
+    k_moves = 1 if rng.random() < 0.6 else rng.choice((2, 3))
+    what = [mutate(cand_o, cand_y) for _ in range(k_moves)]
+    if None in what:
+        continue
+    what = "+".join(what)
     try:
         t, h = evaluate(cand_o, cand_y)
     except (SystemExit, AssertionError):
@@ -110,6 +117,6 @@ while time.time() < t_end:
     if t < best_t - 0.015:
         best_t, order, yields = t, cand_o, cand_y
         accepted += 1
-        print(f"{evals:4d} {what:14s} -> {best_t:.3f} ms", flush=True)
+        print(f"{evals:4d} {what:28s} -> {best_t:.3f} ms", flush=True)
 print(json.dumps({"kernel": kernel, "evals": evals, "accepted": accepted, "ptxas_ms": t_ptxas, "best_ms": best_t,
                   "order": order, "yield_mask": "".join(str(y) for y in yields)}))
