@@ -44,6 +44,12 @@ def test_post_link_scheduling_pass_ran_and_its_checks_hold(pkg):
                          "adds_cta_kernelILi256ELi8ELi2ELi0E", "identity", "--loop=uniform", "--mark",
                          "--out=/dev/null"], capture_output=True, text=True)
     assert r2.returncode != 0 and "marker" in (r2.stdout + r2.stderr)
+    # the measured plans the Makefile applies are permutations with one yield bit per instruction
+    import json
+    for name, n_instr in (("sched_plan_n2048.json", 118), ("sched_plan_n1024.json", 62), ("sched_plan_n512.json", 62)):
+        plan = json.load(open(csrc / name))
+        assert sorted(plan["order"]) == list(range(n_instr)) and len(plan["yield_mask"]) == n_instr
+        assert plan["order"][-1] == n_instr - 1 and plan["best_ms"] < plan["ptxas_ms"]
 
 
 def test_no_cpu_fallback(pkg):
