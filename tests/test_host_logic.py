@@ -44,6 +44,24 @@ def test_post_link_scheduling_pass_ran_and_its_checks_hold(pkg):
                          "adds_cta_kernelILi256ELi8ELi2ELi0E", "identity", "--loop=uniform", "--mark",
                          "--out=/dev/null"], capture_output=True, text=True)
     assert r2.returncode != 0 and "marker" in (r2.stdout + r2.stderr)
+    # an order that lets a minimum cross the packed op that overwrites its operand is refused
+    sys.path.insert(0, str(csrc))
+    try:
+        import sass_sched as S
+    finally:
+        sys.path.pop(0)
+    body = S.pick_loop(S.load(pkg.core.SO_PATH, "adds_cta_kernelILi512ELi4ELi2ELi0E"), "uniform")
+    order = S.make_order(body, "spaced=FADD2:2")
+    S.check_order(body, order)
+    stalls, _ = S.assign_stalls(body, order, 1)
+    assert all(1 <= x <= 15 for x in stalls)
+    first_min = next(p for p, k in enumerate(order) if S.movable(body[k]))
+    writer = next(p for p in range(first_min + 1, len(order))
+                  if S.conflicts(body[order[first_min]], body[order[p]]))
+    bad = list(order)
+    bad.insert(writer, bad.pop(first_min))      # now behind the instruction it conflicts with
+    with pytest.raises(SystemExit):
+        S.check_order(body, bad)
     # the measured plans the Makefile applies are permutations with one yield bit per instruction
     import json
     for name, n_instr in (("sched_plan_n2048.json", 118), ("sched_plan_n1024.json", 62), ("sched_plan_n512.json", 62)):
