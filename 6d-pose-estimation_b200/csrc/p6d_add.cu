@@ -204,7 +204,7 @@ __device__ __forceinline__ float2 pair_sq(float px, float py, float pz, float2 g
 // Software-pipelined form of the unit-stride scan (one quad per trip): the minima of trip t are
 // taken during trip t+1, so their operands are ready from the top of the loop body and their
 // position between the packed ops is free.  ptxas parks them at the top; the post-link pass
-// tools/sass_sched.py (run by the Makefile) spreads them behind FADD2s, which is measurably the
+// csrc/sass_sched.py (run by the Makefile) spreads them behind FADD2s, which is measurably the
 // cheapest place on B200 (NOTES.md).  The arithmetic per pair and the set of values that enter each
 // minimum are the same as in scan_quads, so every bit of the result is too.
 template <int K>
@@ -459,7 +459,7 @@ static const AddsVariant g_adds_variants[] = {
     // flight and hide each other's per-pose latencies (scheduler atomic, parameter loads, barriers)
     {"T256_K4_B4_U2", 256, (const void*)adds_cta_kernel<256, 4, 4, 2>},
     {"T128_K4_B8_U2", 128, (const void*)adds_cta_kernel<128, 4, 8, 2>},
-    // 7, 8: software-pipelined minima (U = 0), re-scheduled after linking by tools/sass_sched.py
+    // 7, 8: software-pipelined minima (U = 0), re-scheduled after linking by csrc/sass_sched.py
     {"T512_K4_B2_D", 512, (const void*)adds_cta_kernel<512, 4, 2, 0>},
     {"T256_K8_B2_D", 256, (const void*)adds_cta_kernel<256, 8, 2, 0>},
     // 9, 10: the small-mesh shapes (5, 6) with software-pipelined minima, re-laid like 8

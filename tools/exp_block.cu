@@ -23,7 +23,7 @@
 // MODE 3: like 2 with FMNMX3
 // MODE 4: no split, 2-source minima in source order (= exp_order ORDER 5)
 // MODE 5: no split, 2-source minima of the PREVIOUS trip (software pipelined: their inputs are ready from
-//         the top of the body, so a post-pass (tools/sass_sched.py) is free to place them anywhere)
+//         the top of the body, so a post-pass (csrc/sass_sched.py) is free to place them anywhere)
 // MODE 6: like 5 with FMNMX3
 template <int T, int K, int MINB, int MODE>
 __global__ void __launch_bounds__(T, MINB) scan_kernel(const float* __restrict__ g, int nquads, int reps, float* out, int flag) {

@@ -1,4 +1,4 @@
-// exp_cubin.cu -- dev harness: load a (possibly re-scheduled, tools/sass_sched.py) cubin of
+// exp_cubin.cu -- dev harness: load a (possibly re-scheduled, csrc/sass_sched.py) cubin of
 // tools/exp_block.cu through the driver API, time one scan kernel and print a checksum.
 // Build: nvcc -O2 -o exp_cubin exp_cubin.cu -lcuda
 // Usage: exp_cubin FILE.cubin MANGLED_KERNEL T K [label]
