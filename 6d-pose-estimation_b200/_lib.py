@@ -25,13 +25,17 @@ SO_PATH = os.path.join(CSRC, "libp6d.so")
 
 P6D_OK, P6D_EINVAL, P6D_ECUDA, P6D_ENOMEM, P6D_ETOOBIG = 0, -1, -2, -3, -4
 
+P6D_VERSION = 2
+
 EXPORTS = (
     "p6d_version", "p6d_last_error", "p6d_device_info", "p6d_mesh_table_create",
-    "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_adds_schedule", "p6d_add_eval", "p6d_add_eval_host",
+    "p6d_mesh_table_destroy", "p6d_adds_max_points", "p6d_adds_schedule", "p6d_adds_schedule_state",
+    "p6d_adds_selfcheck", "p6d_selftest_sqrt2", "p6d_add_eval", "p6d_add_eval_host",
+    "p6d_add_forward_workspace_bytes", "p6d_add_forward", "p6d_add_backward",
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
-    "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject", "p6d_fp32_microbench",
-    "p6d_adds_timeline", "p6d_add_backward", "p6d_depth_crop_backproject", "p6d_pose_loss_pinhole_fwd_bwd",
-    "p6d_project_points",
+    "p6d_pose_loss_pinhole_fwd_bwd", "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject",
+    "p6d_depth_crop_backproject", "p6d_project_points", "p6d_synth_poses", "p6d_sweep_run",
+    "p6d_adds_tf32_eval", "p6d_fp32_microbench",
 )
 
 
@@ -75,9 +79,21 @@ def lib() -> C.CDLL:
     L.p6d_mesh_table_create.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.POINTER(vp)]
     L.p6d_mesh_table_destroy.argtypes = [vp]
     L.p6d_adds_max_points.argtypes = [i32, C.POINTER(i32)]
-    L.p6d_add_eval.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, C.POINTER(Accumulators), vp]
-    L.p6d_add_eval_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp,
+    L.p6d_adds_schedule_state.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.p6d_adds_selfcheck.argtypes = [vp, i64, C.POINTER(i64)]
+    L.p6d_selftest_sqrt2.argtypes = [i32, C.POINTER(i64)]
+    L.p6d_add_eval.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, C.POINTER(Accumulators), vp]
+    L.p6d_add_eval_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                     C.POINTER(i32)]
+    L.p6d_add_forward_workspace_bytes.argtypes = [vp, i64]
+    L.p6d_add_forward_workspace_bytes.restype = i64
+    L.p6d_add_forward.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]
+    u64 = C.c_uint64
+    L.p6d_synth_poses.argtypes = [u64, i32, i32, i64, i64, f32, f32, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                  i32, vp]
+    L.p6d_sweep_run.argtypes = [vp, vp, i32, vp, i32, i64, i64, i64, i64, u64, vp, f32, f32, vp, vp, vp, vp, i64,
+                                vp, vp, vp, vp, vp, vp, vp, C.POINTER(i32), vp]
+    L.p6d_adds_tf32_eval.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, vp, i32, vp]
     L.p6d_quat_to_mat.argtypes = [vp, i64, vp, i32, vp]
     L.p6d_pose_loss_workspace_bytes.restype = i64
     L.p6d_pose_loss_fwd_bwd.argtypes = [vp, vp, vp, vp, i64, f32, f32, i32, vp, vp, vp, vp, i32, vp]
@@ -89,11 +105,12 @@ def lib() -> C.CDLL:
     L.p6d_fp32_microbench.argtypes = [i32, i32, i32, C.POINTER(f64), C.POINTER(f64)]
     L.p6d_depth_crop_backproject.argtypes = [vp, i32, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp]
     L.p6d_project_points.argtypes = [vp, i32, vp, i32, vp, vp, i64, vp, i32, vp]
-    L.p6d_add_backward.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, f32, vp, vp, vp]
-    L.p6d_adds_timeline.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, C.POINTER(i32)]
+    L.p6d_add_backward.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, f32, vp, vp, vp]
     missing = [n for n in EXPORTS if not hasattr(L, n)]
     if missing:
         raise P6DError(f"{SO_PATH} is stale: missing symbols {missing}; rebuild it")
+    if L.p6d_version() != P6D_VERSION:
+        raise P6DError(f"{SO_PATH} implements ABI version {L.p6d_version()}, this package needs {P6D_VERSION}; rebuild it")
     _lib = L
     return L
 
@@ -128,7 +145,10 @@ def as_cuda_f32(t: torch.Tensor, device: torch.device, shape_tail) -> torch.Tens
     if t.dtype != torch.float32:
         t = t.float()
     t = t.reshape(-1, *shape_tail) if shape_tail else t.reshape(-1)
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:          # a view with a storage offset: the kernels use float4 / float2 loads
+        t = t.clone()
+    return t
 
 
 def require_cuda(device) -> torch.device:
@@ -190,38 +210,52 @@ class MeshTable:
     # -- device-buffer evaluation ---------------------------------------------------
     def evaluate(self, pq, pt, gq, gt, obj, want_adds=True, order=None, acc=None):
         """Launch the evaluation kernels on the current stream.  All tensors must already
-        be contiguous CUDA tensors on this table's device.  Returns (add, adds, hit, valid)
-        device tensors (adds is None when want_adds is False)."""
+        be contiguous CUDA tensors on this table's device.  Returns (add, adds, hit, valid, packed)
+        device tensors (adds is None when want_adds is False); `packed` is the one buffer behind
+        them: add f32 | adds f32 | hit u8 | valid u8 | borderline u8."""
         B = obj.shape[0]
         dev = self.device
-        # one allocation: add f32 | adds f32 | hit u8 | valid u8  -> one D2H copy later
-        out = torch.empty(10 * B + 16, dtype=torch.uint8, device=dev)
+        # one allocation -> one D2H copy later
+        out = torch.empty(11 * B + 16, dtype=torch.uint8, device=dev)
         add = out[: 4 * B].view(torch.float32)
         adds = out[4 * B: 8 * B].view(torch.float32)
         hit = out[8 * B: 9 * B]
         valid = out[9 * B: 10 * B]
+        border = out[10 * B: 11 * B]
         acc_struct = None
         if acc is not None:
             acc_struct = Accumulators(*(ptr(a) for a in acc))
         check(lib().p6d_add_eval(self.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), ptr(order), B,
-                                 ptr(add), ptr(adds) if want_adds else None, ptr(hit), ptr(valid),
+                                 ptr(add), ptr(adds) if want_adds else None, ptr(hit), ptr(valid), ptr(border),
                                  C.byref(acc_struct) if acc_struct is not None else None,
                                  stream_ptr(dev)))
         return add, (adds if want_adds else None), hit, valid, out
 
-    def timeline(self, pq, pt, gq, gt, obj, order=None):
-        """Per-CTA {smid, start_ns, end_ns, poses} of one ADD-S launch (measurement helper)."""
+    def forward_loss(self, pq, pt, gq, gt, obj):
+        """ADDLoss.forward value: one launch, no host synchronisation.  Returns (loss [1] f32,
+        count [1] i32) device tensors."""
         B = obj.shape[0]
         dev = self.device
-        out = torch.empty(10 * B + 16, dtype=torch.uint8, device=dev)
-        tl = np.zeros((4096, 4), np.uint64)
-        n = C.c_int(0)
-        torch.cuda.synchronize(dev)
-        check(lib().p6d_adds_timeline(self.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), ptr(order), B,
-                                      out[:4 * B].data_ptr(), out[4 * B:8 * B].data_ptr(),
-                                      out[8 * B:9 * B].data_ptr(), out[9 * B:10 * B].data_ptr(),
-                                      ptr(tl), 4096, C.byref(n)))
-        return tl[: n.value]
+        L = lib()
+        ws = torch.empty(int(L.p6d_add_forward_workspace_bytes(self.handle, B)) + 16, dtype=torch.uint8, device=dev)
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        count = torch.empty(1, dtype=torch.int32, device=dev)
+        check(L.p6d_add_forward(self.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), B, ptr(loss), ptr(count),
+                                ptr(ws), stream_ptr(dev)))
+        return loss, count
+
+    def schedule_state(self) -> dict:
+        """{'built_relaid': 0/1, 'runtime_state': 0 unchecked / 1 verified / 2 rejected} for this table's
+        mesh-size class (see include/p6d.h, p6d_adds_schedule_state)."""
+        a, b = C.c_int(0), C.c_int(0)
+        check(lib().p6d_adds_schedule_state(self.handle, C.byref(a), C.byref(b)))
+        return {"built_relaid": a.value, "runtime_state": b.value}
+
+    def selfcheck(self, n_poses: int = 592) -> int:
+        """Re-laid vs ptxas-scheduled ADD-S kernel on n_poses seeded poses: differing output bytes."""
+        bad = C.c_int64(0)
+        check(lib().p6d_adds_selfcheck(self.handle, int(n_poses), C.byref(bad)))
+        return bad.value
 
     # -- host-buffer evaluation (end-to-end path) -------------------------------------
     def evaluate_host(self, pq, pt, gq, gt, obj, want_adds=True, per_pose=True):
@@ -237,29 +271,37 @@ class MeshTable:
         adds = np.empty(B, np.float32) if (per_pose and want_adds) else None
         hit = np.empty(B, np.uint8) if per_pose else None
         valid = np.empty(B, np.uint8) if per_pose else None
+        border = np.empty(B, np.uint8) if per_pose else None
         ns = self.n_slots
         a_hits, a_valid = np.zeros(ns, np.int64), np.zeros(ns, np.int64)
         a_add, a_adds = np.zeros(ns, np.float64), np.zeros(ns, np.float64)
         launches = C.c_int(0)
         check(lib().p6d_add_eval_host(self.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), B,
-                                      1 if want_adds else 0, ptr(add), ptr(adds), ptr(hit), ptr(valid),
+                                      1 if want_adds else 0, ptr(add), ptr(adds), ptr(hit), ptr(valid), ptr(border),
                                       ptr(a_hits), ptr(a_valid), ptr(a_add), ptr(a_adds), C.byref(launches)))
-        return {"add": add, "adds": adds, "hit": hit, "valid": valid, "obj_hits": a_hits,
+        return {"add": add, "adds": adds, "hit": hit, "valid": valid, "borderline": border, "obj_hits": a_hits,
                 "obj_valid": a_valid, "obj_add_sum": a_add, "obj_adds_sum": a_adds,
                 "gpu_launches": launches.value,
                 "h2d_bytes": B * (16 + 16 + 12 + 12 + 8),
-                "d2h_bytes": (B * (4 + (4 if want_adds else 0) + 2) if per_pose else 0) + 32 * ns}
+                "d2h_bytes": (B * (4 + (4 if want_adds else 0) + 3) if per_pose else 0) + 32 * ns}
 
 
 def add_backward(saved, grad_out):
-    """Gradients of ADDLoss.forward w.r.t. (pred_r, pred_t) through p6d_add_backward."""
-    pq, pt, gq, gt, obj, _is_sym, _keep, count, table, dev = saved
+    """Gradients of ADDLoss.forward w.r.t. (pred_r, pred_t) through p6d_add_backward; the number of
+    valid samples stays on the device (written by p6d_add_forward)."""
+    pq, pt, gq, gt, obj, count, table, dev = saved
     go = grad_out.detach().to(dev, torch.float32).reshape(1).contiguous()
     gq_out = torch.empty_like(pq)
     gt_out = torch.empty_like(pt)
     check(lib().p6d_add_backward(table.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), obj.shape[0], ptr(go),
-                                 1.0 / float(count), ptr(gq_out), ptr(gt_out), stream_ptr(dev)))
+                                 ptr(count), 0.0, ptr(gq_out), ptr(gt_out), stream_ptr(dev)))
     return gq_out, gt_out
+
+
+def selftest_sqrt2(device=0) -> int:
+    bad = C.c_int64(0)
+    check(lib().p6d_selftest_sqrt2(int(device), C.byref(bad)))
+    return bad.value
 
 
 def device_info(device=0) -> dict:

@@ -3,7 +3,9 @@
 The reference-shaped modules live in ``models/`` and ``utils/`` so that adding this
 directory to ``sys.path`` makes ``from models.add_loss import ADDLoss`` resolve here
 (drop-in).  In that layout they are top-level packages and cannot use relative imports to
-reach ``_lib.py``; this helper loads it by path once and caches it in ``sys.modules``.
+reach ``_lib.py``; this helper (importable as ``.._p6d_bootstrap`` inside the package and as
+top-level ``_p6d_bootstrap`` in the drop-in layout) loads it by path once and caches it in
+``sys.modules``.
 """
 import importlib.util
 import os

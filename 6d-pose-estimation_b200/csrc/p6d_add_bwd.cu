@@ -9,6 +9,8 @@
 //   loss = (1/count) * sum_b mean_i d_bi ,  d = |p_i - g_i| (ADD) or min_j |p_i - g_j| (ADD-S)
 //   dL/dp_i = scale * (p_i - g*) / d   (0 where d == 0, PyTorch's norm sub-gradient)
 // Training-size problem (B = 32, N = 500): latency matters, throughput does not.
+#include <mutex>
+
 #include "p6d_common.cuh"
 
 namespace p6d {
@@ -26,6 +28,7 @@ struct BwdArgs {
     const int64_t* obj;
     int64_t B;
     const float* grad_out;  // device scalar (upstream gradient of the 0-d loss)
+    const int32_t* count;   // device: number of valid samples (nullable -> inv_count)
     float inv_count;        // 1 / number of valid samples
     float* grad_q;          // [B,4]
     float* grad_t;          // [B,3]
@@ -66,7 +69,7 @@ __global__ void __launch_bounds__(BWD_T) add_backward_kernel(BwdArgs a, int nmax
         __syncthreads();  // previous pose's scan is done with s_g / s_red
         for (int i = tid; i < n; i += BWD_T) {
             float x, y, z;
-            xform_point(s.xform_mode, __ldg(mx + i), __ldg(my + i), __ldg(mz + i), Rg, tg, x, y, z);
+            xform_point(s.xform_bmm, __ldg(mx + i), __ldg(my + i), __ldg(mz + i), Rg, tg, x, y, z);
             gx[i] = x; gy[i] = y; gz[i] = z;
         }
         __syncthreads();
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(BWD_T) add_backward_kernel(BwdArgs a, int nmax
         for (int i = tid; i < n; i += BWD_T) {
             const float m0 = __ldg(mx + i), m1 = __ldg(my + i), m2 = __ldg(mz + i);
             float px, py, pz;
-            xform_point(s.xform_mode, m0, m1, m2, Rp, tp, px, py, pz);
+            xform_point(s.xform_bmm, m0, m1, m2, Rp, tp, px, py, pz);
             int js = i;
             if (s.symmetric) {
                 float best = __int_as_float(0x7f800000);
@@ -115,7 +118,8 @@ __global__ void __launch_bounds__(BWD_T) add_backward_kernel(BwdArgs a, int nmax
                 for (int w = 0; w < BWD_T / 32; ++w) v += s_red[w][k];
                 t[k] = v;
             }
-            const double scale = (double)__ldg(a.grad_out) * (double)a.inv_count / (double)n;
+            const double inv_count = a.count ? (__ldg(a.count) > 0 ? 1.0 / (double)__ldg(a.count) : 0.0) : (double)a.inv_count;
+            const double scale = (double)__ldg(a.grad_out) * inv_count / (double)n;
             const double x = q[0], y = q[1], z = q[2], w = q[3];
             const double* R = t + 3;  // dL/dR row-major (unscaled)
             const double gxq = 2 * y * R[1] + 2 * z * R[2] + 2 * y * R[3] - 4 * x * R[4] - 2 * w * R[5] + 2 * z * R[6] +
@@ -142,7 +146,7 @@ using namespace p6d;
 
 extern "C" int p6d_add_backward(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
                                 const float* gt, const int64_t* obj, int64_t B, const float* grad_out,
-                                float inv_count, float* grad_q, float* grad_t, void* stream) {
+                                const int32_t* count, float inv_count, float* grad_q, float* grad_t, void* stream) {
     if (!table || B < 0 || (B > 0 && (!pq || !pt || !gq || !gt || !obj || !grad_out || !grad_q || !grad_t))) {
         set_error("p6d_add_backward: bad arguments");
         return P6D_EINVAL;
@@ -158,8 +162,18 @@ extern "C" int p6d_add_backward(const p6d_mesh_table* table, const float* pq, co
         set_error("p6d_add_backward: mesh of %d points does not fit shared memory", nmax);
         return P6D_ETOOBIG;
     }
-    P6D_CUDA(cudaFuncSetAttribute(add_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    BwdArgs a{table->d_soa, table->d_slots, table->n_slots, pq, pt, gq, gt, obj, B, grad_out, inv_count, grad_q, grad_t};
+    {
+        // the attribute is a per-device maximum shared by every table and thread: only ever raise it
+        static std::mutex mu;
+        static size_t raised[64];
+        std::lock_guard<std::mutex> lock(mu);
+        size_t& cur = raised[table->device & 63];
+        if (smem > cur) {
+            P6D_CUDA(cudaFuncSetAttribute(add_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cur = smem;
+        }
+    }
+    BwdArgs a{table->d_soa, table->d_slots, table->n_slots, pq, pt, gq, gt, obj, B, grad_out, count, inv_count, grad_q, grad_t};
     int64_t grid = B < (int64_t)table->sm_count * 4 ? B : (int64_t)table->sm_count * 4;
     add_backward_kernel<<<(unsigned)grid, BWD_T, smem, static_cast<cudaStream_t>(stream)>>>(a, nmax);
     P6D_CUDA(cudaGetLastError());

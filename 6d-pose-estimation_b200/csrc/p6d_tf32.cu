@@ -1,0 +1,355 @@
+// p6d_tf32.cu -- GEMM-form ADD-S on the 5th-generation tensor cores (tcgen05, kind::tf32).
+//
+// OPT-IN EVIDENCE KERNEL, never on the product path.  BASELINE.json's north_star excludes tensor
+// cores from kernel (b) "unless a 3xTF32 variant passes the stated tolerance" (1e-5 relative on
+// distances, bit-exact ADD-0.1d decisions).  This file is that variant, written for real so that the
+// exclusion rests on measurements (tests/test_tf32_variant.py) instead of on an error estimate:
+//
+//   d^2(i,j) = |p_i|^2 + |g_j|^2 - 2 p_i.g_j      (reference: models/add_loss.py:185-190 computes
+//                                                  |p_i - g_j| directly, which has no cancellation)
+//
+// Per pose: both clouds are transformed exactly like the product kernel (reference rounding), then
+// re-centred on the gt translation (rounded to 2^-8 m so that the subtraction is exact or nearly so --
+// camera-frame coordinates of ~1 m would cost another two decimal digits).  The cross term and the
+// |g_j|^2 term go through ONE tensor-core GEMM  S = A B^T  with K = 16:
+//     A row i = [ ph  ph  pl | 1 1 1 | 0 ],   B row j = [ -2gh  -2gl  -2gh | G2h G2m G2l | 0 ]
+// (x = xh + xl the two-term TF32 split, G2 = |g_j|^2 split into three TF32 terms; "3xTF32": the
+// product pl.gl is dropped, as in the usual error-compensated scheme), FP32 accumulation in TMEM.
+// The epilogue reads S back with tcgen05.ld, takes the row minima (FMNMX3), adds |p_i|^2 in FP32
+// and takes one square root per pred point.  split_terms = 1 runs plain TF32 (no low parts).
+//
+// Mechanics: one CTA (128 threads) per pose, grid-stride.  B operand (all gt points, 64 B per
+// point) resident in shared memory in the canonical K-major no-swizzle UMMA layout; A operand of
+// the current 128-row tile double-buffered; D = 128 x 256 FP32 in TMEM, two accumulators (512
+// columns) so that the MMAs of tile t+1 run under the epilogue of tile t.  One elected thread issues
+// tcgen05.mma (M = 128, N = 256, K = 8, two k-steps per tile) and tcgen05.commit onto an mbarrier.
+#include "p6d_common.cuh"
+
+namespace p6d {
+
+constexpr int TF_T = 128;           // threads = TMEM lanes = rows of one M tile
+constexpr int TF_N = 256;           // columns of one MMA / accumulator
+constexpr int TF_ROW_BYTES = 64;    // K = 16 TF32 per operand row
+
+__device__ __forceinline__ float tf32_rn(float x) {
+    // round to nearest (ties away) onto the 10-bit TF32 mantissa; the low 13 bits come out zero,
+    // so the tensor core's own truncation of the FP32 pattern cannot change the value
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// byte offset of element k of row r in the canonical K-major no-swizzle layout:
+// 8 rows x 16 B form one contiguous 128-B core matrix; the four K chunks of an 8-row group follow
+// each other (LBO = 128 B); 8-row groups are 512 B apart (SBO = 512 B)
+__device__ __forceinline__ uint32_t operand_offset(int r, int k) {
+    return static_cast<uint32_t>((r >> 3) * 512 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4);
+}
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);          // start address, 16-B units
+    d |= static_cast<uint64_t>(128u >> 4) << 16;                      // leading (K) byte offset
+    d |= static_cast<uint64_t>(512u >> 4) << 32;                      // stride (M/N) byte offset
+    d |= 1ull << 46;                                                  // descriptor version (Blackwell)
+    return d;                                                         // base offset 0, no swizzle
+}
+
+// kind::tf32, D = F32, A and B K-major, M = 128, N = 256
+constexpr uint32_t TF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((TF_N >> 3) << 17) | ((TF_T >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(TF_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// bounded wait: a malformed descriptor must end in an error, not in a hung GPU
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// 32 consecutive accumulator columns of this thread's row
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+struct Tf32Args {
+    const float* soa;
+    const SlotInfo* slots;
+    int n_slots;
+    const float* pq;
+    const float* pt;
+    const float* gq;
+    const float* gt;
+    const int64_t* obj;
+    int64_t B;
+    int split_terms;   // 1 = plain TF32, 3 = 3xTF32
+    float* adds;
+    int* error_flag;   // set to 1 when an mbarrier wait ran out (kernel then stops doing work)
+};
+
+__global__ void __launch_bounds__(TF_T, 1) adds_tf32_kernel(Tf32Args a, int nb_max) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* s_b = smem_raw;                                       // [nb_max rows x 64 B]
+    unsigned char* s_a = smem_raw + static_cast<size_t>(nb_max) * TF_ROW_BYTES;   // 2 x [128 rows x 64 B]
+    __shared__ uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ double s_red[TF_T / 32];
+    __shared__ int s_fail;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+        s_fail = 0;
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+    uint32_t uses[2] = {0, 0};          // completed phases of the two accumulator barriers
+
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const int64_t oid = a.obj[b];
+        const bool known = oid >= 0 && oid < a.n_slots && a.slots[oid].count > 0;
+        if (!known || s_fail) {          // CTA-uniform
+            if (tid == 0) a.adds[b] = 0.0f;
+            continue;
+        }
+        const SlotInfo s = a.slots[oid];
+        const int n = s.count;
+        const float* mx = a.soa + s.soa_offset;
+        const float* my = mx + s.padded;
+        const float* mz = my + s.padded;
+        float Rp[9], Rg[9], tp[3], tg[3], c[3], q[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(a.pq + 4 * b + k);
+        quat_to_mat(q, Rp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q[k] = __ldg(a.gq + 4 * b + k);
+        quat_to_mat(q, Rg);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            tp[k] = __ldg(a.pt + 3 * b + k);
+            tg[k] = __ldg(a.gt + 3 * b + k);
+            c[k] = rintf(tg[k] * 256.0f) * (1.0f / 256.0f);     // centre: gt translation on a 2^-8 m grid
+        }
+        const int n_tiles_n = (n + TF_N - 1) / TF_N, n_tiles_m = (n + TF_T - 1) / TF_T;
+        const bool three = a.split_terms >= 3;
+
+        // ---- B operand: every gt point, re-centred, split
+        for (int j = tid; j < n_tiles_n * TF_N; j += TF_T) {
+            float row[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) row[k] = 0.0f;
+            if (j < n) {
+                float g[3];
+                xform_point(s.xform_mode, __ldg(mx + j), __ldg(my + j), __ldg(mz + j), Rg, tg, g[0], g[1], g[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[k] = __fsub_rn(g[k], c[k]);
+                const float g2 = sq3(g[0], g[1], g[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float h = tf32_rn(g[k]);
+                    const float l = tf32_rn(__fsub_rn(g[k], h));
+                    row[k] = -2.0f * h;
+                    if (three) {
+                        row[3 + k] = -2.0f * l;
+                        row[6 + k] = -2.0f * h;
+                    }
+                }
+                const float h = tf32_rn(g2), m = tf32_rn(__fsub_rn(g2, h));
+                row[9] = h;
+                row[10] = m;
+                row[11] = tf32_rn(__fsub_rn(__fsub_rn(g2, h), m));
+            } else {
+                row[9] = 1.0e30f;       // padding: never the minimum (TF32-representable after rounding)
+                row[9] = tf32_rn(row[9]);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch)
+                *reinterpret_cast<float4*>(s_b + operand_offset(j, 4 * ch)) =
+                    make_float4(row[4 * ch], row[4 * ch + 1], row[4 * ch + 2], row[4 * ch + 3]);
+        }
+
+        double acc = 0.0;
+        for (int mt = 0; mt < n_tiles_m; ++mt) {
+            // ---- A operand of this tile: pred point of this thread
+            unsigned char* a_buf = s_a + (mt & 1) * TF_T * TF_ROW_BYTES;
+            const int i = mt * TF_T + tid;
+            float pn = 0.0f;
+            {
+                float row[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) row[k] = 0.0f;
+                if (i < n) {
+                    float p[3];
+                    xform_point(s.xform_mode, __ldg(mx + i), __ldg(my + i), __ldg(mz + i), Rp, tp, p[0], p[1], p[2]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p[k] = __fsub_rn(p[k], c[k]);
+                    pn = sq3(p[0], p[1], p[2]);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float h = tf32_rn(p[k]);
+                        row[k] = h;
+                        if (three) {
+                            row[3 + k] = h;
+                            row[6 + k] = tf32_rn(__fsub_rn(p[k], h));
+                        }
+                    }
+                    row[9] = row[10] = row[11] = 1.0f;
+                }
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    *reinterpret_cast<float4*>(a_buf + operand_offset(tid, 4 * ch)) =
+                        make_float4(row[4 * ch], row[4 * ch + 1], row[4 * ch + 2], row[4 * ch + 3]);
+            }
+            fence_proxy_async();        // generic-proxy writes (A, and B on the first tile) -> async proxy (tensor core)
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+
+            float m = __int_as_float(0x7f800000);
+            const uint32_t a_addr = smem_u32(a_buf), b_addr = smem_u32(s_b);
+            auto issue = [&](int nt) {
+                const uint32_t d = tmem + static_cast<uint32_t>((nt & 1) * TF_N);
+                const uint32_t bt = b_addr + static_cast<uint32_t>(nt) * (TF_N / 8) * 512;
+                umma_tf32(d, smem_desc(a_addr), smem_desc(bt), 0u);
+                umma_tf32(d, smem_desc(a_addr + 256), smem_desc(bt + 256), 1u);   // second k-step: K chunks 2, 3
+                umma_commit(&s_bar[nt & 1]);
+            };
+            if (tid == 0) issue(0);
+            for (int nt = 0; nt < n_tiles_n; ++nt) {
+                // accumulator (nt+1)&1 was drained by every warp in the previous trip (barrier below)
+                if (tid == 0 && nt + 1 < n_tiles_n) issue(nt + 1);
+                const int k = nt & 1;
+                if (!mbar_wait_bounded(&s_bar[k], uses[k] & 1)) s_fail = 1;
+                ++uses[k];
+                tc_fence_after();
+                if (!s_fail) {
+                    const uint32_t row_addr = tmem + (static_cast<uint32_t>(warp * 32) << 16) + static_cast<uint32_t>(k * TF_N);
+#pragma unroll 1
+                    for (int col = 0; col < TF_N; col += 32) {
+                        float v[32];
+                        tmem_ld32(row_addr + col, v);
+#pragma unroll
+                        for (int e = 0; e < 32; e += 2) m = min3_nan(m, v[e], v[e + 1]);
+                    }
+                }
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
+            }
+            if (i < n) {
+                const float d2 = __fadd_rn(pn, m);
+                acc += static_cast<double>(__fsqrt_rn(d2 > 0.0f ? d2 : 0.0f));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < TF_T / 32; ++w) t += s_red[w];
+            a.adds[b] = static_cast<float>(t / static_cast<double>(n));
+        }
+        __syncthreads();
+    }
+    if (tid == 0 && s_fail) *a.error_flag = 1;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    }
+}
+
+}  // namespace p6d
+
+using namespace p6d;
+
+extern "C" int p6d_adds_tf32_eval(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                                  const float* gt, const int64_t* obj, int64_t B, int split_terms, float* adds,
+                                  int max_ctas, void* stream) {
+    if (!table || B < 0 || (split_terms != 1 && split_terms != 3) ||
+        (B > 0 && (!pq || !pt || !gq || !gt || !obj || !adds))) {
+        set_error("p6d_adds_tf32_eval: bad arguments");
+        return P6D_EINVAL;
+    }
+    if (B == 0) return P6D_OK;
+    DeviceGuard guard(table->device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb_max = (table->max_count + TF_N - 1) / TF_N * TF_N;
+    const size_t smem = static_cast<size_t>(nb_max) * TF_ROW_BYTES + 2 * TF_T * TF_ROW_BYTES;
+    int limit = 0;
+    P6D_CUDA(cudaDeviceGetAttribute(&limit, cudaDevAttrMaxSharedMemoryPerBlockOptin, table->device));
+    if (smem + 1024 > static_cast<size_t>(limit)) {
+        set_error("p6d_adds_tf32_eval: mesh of %d points does not fit shared memory", table->max_count);
+        return P6D_ETOOBIG;
+    }
+    P6D_CUDA(cudaFuncSetAttribute(adds_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int* d_flag = nullptr;
+    P6D_CUDA(cudaMalloc(&d_flag, sizeof(int)));
+    P6D_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    Tf32Args a{table->d_soa, table->d_slots, table->n_slots, pq, pt, gq, gt, obj, B, split_terms, adds, d_flag};
+    int64_t grid = table->sm_count;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid > B) grid = B;
+    adds_tf32_kernel<<<static_cast<unsigned>(grid), TF_T, smem, st>>>(a, nb_max);
+    cudaError_t e = cudaGetLastError();
+    int flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_flag);
+    if (e != cudaSuccess) return cuda_fail(e, "adds_tf32_kernel");
+    if (flag) {
+        set_error("p6d_adds_tf32_eval: a tensor-core completion barrier timed out");
+        return P6D_ECUDA;
+    }
+    return P6D_OK;
+}

@@ -8,24 +8,17 @@ ops.  One kernel launch and one device->host copy per ``eval_metrics`` call repl
 
 There is no CPU path: the device must be CUDA.
 """
-import importlib.util
 import os
-import sys
 
 import numpy as np
 import torch
 import torch.nn as nn
 
 
-def _core():
-    mod = sys.modules.get("p6d_b200_core")
-    if mod is None:
-        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        spec = importlib.util.spec_from_file_location("p6d_b200_bootstrap", os.path.join(here, "_bootstrap.py"))
-        boot = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(boot)
-        mod = boot.core()
-    return mod
+try:                                    # imported as part of the package ...
+    from .._p6d_bootstrap import core as _core
+except ImportError:                     # ... or as top-level `models` / `utils` (drop-in layout: this
+    from _p6d_bootstrap import core as _core   # directory is at the front of sys.path, see dropin.py)
 
 
 # eggbox and glue (reference add_loss.py:10)
@@ -52,19 +45,22 @@ def _read_ascii_ply(path):
 
 
 class _AddForward(torch.autograd.Function):
-    """Attaches the fused backward (p6d_add_backward) to an already computed loss value."""
+    """ADDLoss.forward as one launch (p6d_add_forward) with the fused backward
+    (p6d_add_backward) attached; nothing is read back to the host on either side."""
 
     @staticmethod
-    def forward(ctx, value, crit, saved, pred_r, pred_t):
-        ctx.crit, ctx.saved = crit, saved
+    def forward(ctx, pred_r, pred_t, crit, prepared):
+        dev, pq, pt, gq, gt, obj, table = prepared
+        loss, count = table.forward_loss(pq, pt, gq, gt, obj)
+        ctx.saved = (pq, pt, gq, gt, obj, count, table, dev)
         ctx.shapes = (pred_r.shape, pred_t.shape, pred_r.dtype, pred_t.dtype)
-        return value.clone()
+        return loss.reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        gq, gt = ctx.crit._forward_grads(ctx.saved, grad_out)
+        gq, gt = _core().add_backward(ctx.saved, grad_out)
         rs, ts, rd, td = ctx.shapes
-        return None, None, None, gq.reshape(rs).to(rd), gt.reshape(ts).to(td)
+        return gq.reshape(rs).to(rd), gt.reshape(ts).to(td), None, None
 
 
 class ADDLoss(nn.Module):
@@ -79,6 +75,9 @@ class ADDLoss(nn.Module):
         self.trans_weight = trans_weight
         self._table = None
         self._table_key = None
+        # optional callable(indices, pred_r, pred_t, gt_r, gt_t, obj_ids) -> 0/1 per index, consulted by
+        # eval_metrics for decisions flagged `borderline`; None (default): the kernel's decision stands
+        self.borderline_resolver = None
         self._load_models(model_dir)
 
     # ------------------------------------------------------------------ loading
@@ -142,7 +141,7 @@ class ADDLoss(nn.Module):
             self._table_key = key
         return self._table
 
-    def _prepare(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
+    def _prepare(self, pred_r, pred_t, gt_r, gt_t, obj_ids, sort=True):
         core = _core()
         dev = self._cuda_device(pred_r if isinstance(pred_r, torch.Tensor) else None)
         pq = core.as_cuda_f32(pred_r, dev, (4,))
@@ -155,7 +154,7 @@ class ADDLoss(nn.Module):
         if not (pq.shape[0] == pt.shape[0] == gq.shape[0] == gt.shape[0] == B):
             raise ValueError("pred_r, pred_t, gt_r, gt_t and obj_ids must share the batch dimension")
         order = None
-        if B >= _SORT_THRESHOLD:
+        if sort and B >= _SORT_THRESHOLD:
             order = torch.argsort(obj, stable=True).to(torch.int32)
         return dev, pq, pt, gq, gt, obj, order
 
@@ -168,77 +167,65 @@ class ADDLoss(nn.Module):
         keep = per_pose["valid"].astype(bool)
         if not keep.any():
             return {"add_mean": 0, "add_s_mean": 0, "add_01d_acc": 0}
+        hit = per_pose["hit"]
+        if self.borderline_resolver is not None and per_pose["borderline"].any():
+            # decisions within 4 ulp of the threshold: let the caller's own reference decide
+            # (tests/ use the torch-eager restatement on the host)
+            idx = np.nonzero(per_pose["borderline"] & per_pose["valid"])[0]
+            if idx.size:
+                hit = hit.copy()
+                hit[idx] = np.asarray(self.borderline_resolver(idx, pred_r, pred_t, gt_r, gt_t, obj_ids), np.uint8)
         # the reference averages Python floats on the host: float64 np.mean
         return {
             "add_mean": np.mean(per_pose["add"][keep].astype(np.float64)) * 1000,
             "add_s_mean": np.mean(per_pose["add_s"][keep].astype(np.float64)) * 1000,
-            "add_01d_acc": np.mean(per_pose["hit"][keep].astype(np.float64)) * 100,
+            "add_01d_acc": np.mean(hit[keep].astype(np.float64)) * 100,
         }
 
     @torch.no_grad()
     def eval_poses(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
-        """Per-pose float32 ADD, ADD-S, uint8 hit / valid as NumPy arrays (one launch,
-        one device->host copy).  Addition to the reference surface."""
+        """Per-pose float32 ADD, ADD-S, uint8 hit / valid / borderline as NumPy arrays (one
+        launch, one device->host copy).  Addition to the reference surface.  ``borderline`` marks
+        decisions whose distance lies within 4 float32 ulp of 0.1*diameter."""
         dev, pq, pt, gq, gt, obj, order = self._prepare(pred_r, pred_t, gt_r, gt_t, obj_ids)
         B = obj.shape[0]
         if B == 0 or not self.points:
             z = np.zeros(B, np.float32)
-            return {"add": z, "add_s": z.copy(), "hit": np.zeros(B, np.uint8), "valid": np.zeros(B, np.uint8)}
+            zb = np.zeros(B, np.uint8)
+            return {"add": z, "add_s": z.copy(), "hit": zb, "valid": zb.copy(), "borderline": zb.copy()}
         table = self._mesh_table(dev)
         _, _, _, _, packed = table.evaluate(pq, pt, gq, gt, obj, True, order)
         host = packed.cpu().numpy()       # the only synchronisation of the call
         return {"add": host[:4 * B].view(np.float32), "add_s": host[4 * B:8 * B].view(np.float32),
-                "hit": host[8 * B:9 * B], "valid": host[9 * B:10 * B]}
+                "hit": host[8 * B:9 * B], "valid": host[9 * B:10 * B], "borderline": host[10 * B:11 * B]}
 
     # ------------------------------------------------------------------ differentiable loss
     def forward(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
-        """Mean over valid samples of ADD (asymmetric ids) or ADD-S (symmetric ids);
-        0-d tensor; a ``requires_grad`` zero when no sample has a mesh (reference :101-150)."""
-        value, saved = self._forward_value(pred_r, pred_t, gt_r, gt_t, obj_ids)
-        if saved is None:
-            return value
+        """Mean over valid samples of ADD (asymmetric ids) or ADD-S (symmetric ids); 0-d tensor
+        (reference :101-150).  ONE kernel launch, no host synchronisation: the reference's grouping
+        (objects in order of first appearance, float32 sum per group, total / count) happens on the
+        device.  When no sample has a mesh the value is 0 and, like the reference's fresh
+        ``tensor(0.0, requires_grad=True)``, carries no gradient to the inputs."""
+        dev, pq, pt, gq, gt, obj, _ = self._prepare(pred_r, pred_t, gt_r, gt_t, obj_ids, sort=False)
+        if obj.shape[0] == 0 or not self.points:
+            return torch.tensor(0.0, device=dev).requires_grad_(True)
+        prepared = (dev, pq, pt, gq, gt, obj, self._mesh_table(dev))
         wants_grad = torch.is_grad_enabled() and any(
             isinstance(t, torch.Tensor) and t.requires_grad for t in (pred_r, pred_t))
         if not wants_grad:
-            return value
-        return _AddForward.apply(value, self, saved, pred_r, pred_t)
+            loss, _ = prepared[-1].forward_loss(pq, pt, gq, gt, obj)
+            loss = loss.reshape(())
+            # No input asks for a gradient.  The reference then returns a plain tensor -- except when no
+            # sample has a mesh, where it returns a fresh leaf with requires_grad=True so that a training
+            # loop's .backward() does not raise.  Which case applies is only known on the device, so the
+            # result is a leaf that accepts .backward() in both (deviation: also in the non-empty case).
+            return loss.requires_grad_(True) if torch.is_grad_enabled() else loss
+        pr = pred_r if isinstance(pred_r, torch.Tensor) else torch.as_tensor(pred_r)
+        pt_in = pred_t if isinstance(pred_t, torch.Tensor) else torch.as_tensor(pred_t)
+        return _AddForward.apply(pr, pt_in, self, prepared)
 
     def train_loss(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
         return self.forward(pred_r, pred_t, gt_r, gt_t, obj_ids)
-
-    @torch.no_grad()
-    def _forward_value(self, pred_r, pred_t, gt_r, gt_t, obj_ids):
-        dev, pq, pt, gq, gt, obj, order = self._prepare(pred_r, pred_t, gt_r, gt_t, obj_ids)
-        B = obj.shape[0]
-        if B == 0 or not self.points:
-            return torch.tensor(0.0, device=dev).requires_grad_(True), None
-        table = self._mesh_table(dev)
-        add, adds, _, valid, _ = table.evaluate(pq, pt, gq, gt, obj, True, order)
-        sym = torch.from_numpy(table.symmetric.astype(np.bool_)).to(dev)
-        in_range = (obj >= 0) & (obj < table.n_slots)
-        is_sym = torch.zeros(B, dtype=torch.bool, device=dev)
-        is_sym[in_range] = sym[obj[in_range]]
-        per_sample = torch.where(is_sym, adds, add)
-        keep = valid.bool()
-        count = int(keep.sum().item())
-        if count == 0:
-            return torch.tensor(0.0, device=dev).requires_grad_(True), None
-        # the reference sums per object group (first-appearance order) in float32
-        total = torch.zeros((), dtype=torch.float32, device=dev)
-        seen = []
-        for o in obj[keep].tolist():
-            if o not in seen:
-                seen.append(o)
-        for o in seen:
-            total = total + per_sample[keep & (obj == o)].sum()
-        saved = (pq, pt, gq, gt, obj, is_sym, keep, count, table, dev)
-        return total / count, saved
-
-    def _forward_grads(self, saved, grad_out):
-        core = _core()
-        if saved is None:
-            return None, None
-        return core.add_backward(saved, grad_out)
 
     # ------------------------------------------------------------------ quaternion -> matrix
     def _quat_to_mat(self, q):

@@ -6,23 +6,16 @@ the reference's ``models/pose_loss.py`` (SFR-Vision/6d-pose-estimation).
 ONE kernel launch (``p6d_pose_loss_fwd_bwd``) instead of ~40 eager launches
 (reference ``pose_loss.py:19-61`` + autograd).  CUDA only, no CPU path.
 """
-import importlib.util
 import os
-import sys
 
 import torch
 import torch.nn as nn
 
 
-def _core():
-    mod = sys.modules.get("p6d_b200_core")
-    if mod is None:
-        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        spec = importlib.util.spec_from_file_location("p6d_b200_bootstrap", os.path.join(here, "_bootstrap.py"))
-        boot = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(boot)
-        mod = boot.core()
-    return mod
+try:                                    # imported as part of the package ...
+    from .._p6d_bootstrap import core as _core
+except ImportError:                     # ... or as top-level `models` / `utils` (drop-in layout: this
+    from _p6d_bootstrap import core as _core   # directory is at the front of sys.path, see dropin.py)
 
 
 _workspaces = {}
@@ -36,6 +29,25 @@ def _workspace(dev):
     return ws
 
 
+def _ready(t, dev, tail):
+    """`t` as a contiguous float32 tensor on `dev` -- without touching it when it already is one
+    (the training step: every input comes straight out of the network; each avoided torch op is
+    3-5 us of the ~100 us the Python side of a B = 32 step costs)."""
+    if (isinstance(t, torch.Tensor) and t.dtype is torch.float32 and t.device == dev and t.is_contiguous()
+            and t.data_ptr() % 16 == 0):
+        return t.detach() if t.requires_grad else t
+    return _core().as_cuda_f32(t, dev, tail)
+
+
+def _empty_batch_nan(*tensors):
+    """The reference on an empty batch: mean over zero rows -> NaN, attached to the inputs' graph."""
+    total = None
+    for t in tensors:
+        s = t.sum() * float("nan")
+        total = s if total is None else total + s
+    return total
+
+
 class _FusedPoseLoss(torch.autograd.Function):
     """out = [loss, rot_term, trans_term]; grads for upstream 1 are produced by the
     forward launch and scaled by grad_output in backward."""
@@ -44,35 +56,40 @@ class _FusedPoseLoss(torch.autograd.Function):
     def forward(ctx, pred_rot, pred_trans, gt_rot, gt_trans, rot_weight, trans_weight, mode, pick):
         core = _core()
         dev = core.require_cuda(pred_rot.device)
-        pq = core.as_cuda_f32(pred_rot, dev, (4,))
-        pt = core.as_cuda_f32(pred_trans, dev, (3,))
-        gq = core.as_cuda_f32(gt_rot, dev, (4,))
-        gt = core.as_cuda_f32(gt_trans, dev, (3,))
-        B = pq.shape[0]
-        if not (pt.shape[0] == gq.shape[0] == gt.shape[0] == B) or B == 0:
-            raise ValueError("PoseLoss needs non-empty inputs with a common batch dimension")
+        pq = _ready(pred_rot, dev, (4,))
+        pt = _ready(pred_trans, dev, (3,))
+        gq = _ready(gt_rot, dev, (4,))
+        gt = _ready(gt_trans, dev, (3,))
+        B = pq.numel() // 4
+        if not (pt.numel() == 3 * B and gq.numel() == 4 * B and gt.numel() == 3 * B) or B == 0:
+            raise ValueError("PoseLoss needs inputs with a common batch dimension")
         need_q = ctx.needs_input_grad[0]
         need_t = ctx.needs_input_grad[1]
-        out = torch.empty(3, dtype=torch.float32, device=dev)
-        # both gradients live in one buffer so that backward scales them with one launch
-        flat = torch.empty(7 * B, dtype=torch.float32, device=dev) if (need_q or need_t) else None
-        gq_out = flat[:4 * B] if need_q else None
-        gt_out = flat[4 * B:] if need_t else None
+        # one allocation: [grad_q 4B | grad_t 3B | pad to 4 | loss, rot term, trans term]; both gradients
+        # in one buffer so that backward scales them with one launch
+        gb = (7 * B + 3) // 4 * 4
+        buf = torch.empty(gb + 4, dtype=torch.float32, device=dev)
+        base = buf.data_ptr()
         core.check(core.lib().p6d_pose_loss_fwd_bwd(
-            core.ptr(pq), core.ptr(pt), core.ptr(gq), core.ptr(gt), B, float(rot_weight), float(trans_weight),
-            int(mode), core.ptr(out), core.ptr(gq_out), core.ptr(gt_out), core.ptr(_workspace(dev)),
-            dev.index, core.stream_ptr(dev)))
-        ctx.flat = flat
+            pq.data_ptr(), pt.data_ptr(), gq.data_ptr(), gt.data_ptr(), B, float(rot_weight), float(trans_weight),
+            int(mode), base + 4 * gb, base if need_q else None, base + 16 * B if need_t else None,
+            _workspace(dev).data_ptr(), dev.index, core.stream_ptr(dev)))
+        ctx.buf = buf
         ctx.meta = (pred_rot.shape, pred_trans.shape, pred_rot.dtype, pred_trans.dtype, need_q, need_t, B)
-        return out[pick]
+        return buf[gb + pick]
 
     @staticmethod
     def backward(ctx, grad_out):
         rs, ts, rd, td, need_q, need_t, B = ctx.meta
         # pick 0: d loss; pick 1: d rot_term (the kernel ran with rot_weight 1, trans_weight 0)
-        scaled = ctx.flat * grad_out
-        dq = scaled[:4 * B].reshape(rs).to(rd) if need_q else None
-        dt = scaled[4 * B:].reshape(ts).to(td) if need_t else None
+        scaled = ctx.buf[:7 * B] * grad_out
+        dq = dt = None
+        if need_q:
+            dq = scaled[:4 * B].view(rs)
+            dq = dq if rd is torch.float32 else dq.to(rd)
+        if need_t:
+            dt = scaled[4 * B:].view(ts)
+            dt = dt if td is torch.float32 else dt.to(td)
         return dq, dt, None, None, None, None, None, None
 
 
@@ -84,42 +101,49 @@ class _FusedGeometricPoseLoss(torch.autograd.Function):
     def forward(ctx, pred_rot, z_pred, bbox_center, camera_matrix, gt_rot, gt_trans, rot_weight, trans_weight, mode):
         core = _core()
         dev = core.require_cuda(pred_rot.device)
-        pq = core.as_cuda_f32(pred_rot, dev, (4,))
-        z = core.as_cuda_f32(z_pred, dev, ())
-        uv = core.as_cuda_f32(bbox_center, dev, (2,))
-        gq = core.as_cuda_f32(gt_rot, dev, (4,))
-        gt = core.as_cuda_f32(gt_trans, dev, (3,))
-        B = pq.shape[0]
-        if B == 0 or not (z.shape[0] == uv.shape[0] == gq.shape[0] == gt.shape[0] == B):
+        pq = _ready(pred_rot, dev, (4,))
+        z = _ready(z_pred, dev, ())
+        uv = _ready(bbox_center, dev, (2,))
+        gq = _ready(gt_rot, dev, (4,))
+        gt = _ready(gt_trans, dev, (3,))
+        B = pq.numel() // 4
+        if B == 0 or not (z.numel() == B and uv.numel() == 2 * B and gq.numel() == 4 * B and gt.numel() == 3 * B):
             raise ValueError("forward_geometric needs non-empty inputs with a common batch dimension")
-        K = core.as_cuda_f32(camera_matrix, dev, ())
+        K = _ready(camera_matrix, dev, ())
         if camera_matrix.dim() == 2 and K.numel() == 9:
             kb = 0
         elif camera_matrix.dim() == 3 and K.numel() == 9 * B:
             kb = 1
         else:
             raise ValueError("camera_matrix must be [3,3] or [B,3,3]")
-        out = torch.empty(3, dtype=torch.float32, device=dev)
-        trans = torch.empty(B, 3, dtype=torch.float32, device=dev)
         need_q, need_z = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        flat = torch.empty(5 * B, dtype=torch.float32, device=dev) if (need_q or need_z) else None
-        gq_out = flat[:4 * B] if need_q else None
-        gz_out = flat[4 * B:] if need_z else None
+        # one allocation: [grad_q 4B | grad_z B | pad to 4 | translation 3B | pad to 4 | loss, rot, trans terms]
+        gb = (5 * B + 3) // 4 * 4
+        tb = (3 * B + 3) // 4 * 4
+        buf = torch.empty(gb + tb + 4, dtype=torch.float32, device=dev)
+        base = buf.data_ptr()
         core.check(core.lib().p6d_pose_loss_pinhole_fwd_bwd(
-            core.ptr(pq), core.ptr(z), core.ptr(uv), core.ptr(K), kb, core.ptr(gq), core.ptr(gt), B,
-            float(rot_weight), float(trans_weight), int(mode), core.ptr(out), core.ptr(gq_out), core.ptr(gz_out),
-            core.ptr(trans), core.ptr(_workspace(dev)), dev.index, core.stream_ptr(dev)))
-        ctx.flat = flat
+            pq.data_ptr(), z.data_ptr(), uv.data_ptr(), K.data_ptr(), kb, gq.data_ptr(), gt.data_ptr(), B,
+            float(rot_weight), float(trans_weight), int(mode), base + 4 * (gb + tb), base if need_q else None,
+            base + 16 * B if need_z else None, base + 4 * gb, _workspace(dev).data_ptr(), dev.index,
+            core.stream_ptr(dev)))
+        trans = buf[gb:gb + 3 * B].view(B, 3)
+        ctx.buf = buf
         ctx.meta = (pred_rot.shape, z_pred.shape, pred_rot.dtype, z_pred.dtype, need_q, need_z, B)
         ctx.mark_non_differentiable(trans)
-        return out[0], trans
+        return buf[gb + tb], trans
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_trans):
         rs, zs, rd, zd, need_q, need_z, B = ctx.meta
-        scaled = ctx.flat * grad_loss
-        dq = scaled[:4 * B].reshape(rs).to(rd) if need_q else None
-        dz = scaled[4 * B:].reshape(zs).to(zd) if need_z else None
+        scaled = ctx.buf[:5 * B] * grad_loss
+        dq = dz = None
+        if need_q:
+            dq = scaled[:4 * B].view(rs)
+            dq = dq if rd is torch.float32 else dq.to(rd)
+        if need_z:
+            dz = scaled[4 * B:].view(zs)
+            dz = dz if zd is torch.float32 else dz.to(zd)
         return dq, dz, None, None, None, None, None, None, None
 
 
@@ -137,6 +161,8 @@ class PoseLoss(nn.Module):
         return 0 if self.rotation_loss_type == 'geodesic' else 1
 
     def forward(self, pred_rot, pred_trans, gt_rot, gt_trans, obj_ids=None):
+        if pred_rot.shape[0] == 0:
+            return _empty_batch_nan(pred_rot, pred_trans)
         return _FusedPoseLoss.apply(pred_rot, pred_trans, gt_rot, gt_trans, self.rot_weight,
                                     self.trans_weight, self._mode(), 0)
 

@@ -18,6 +18,8 @@ the caller-side counterpart of the kernels:
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import numpy as np
 import torch
 
@@ -135,71 +137,92 @@ class PoseEvaluator:
         return self.acc.all_reduce(group)
 
 
-def synth_chunk(n: int, seed: int, device, rot_sigma=0.05, trans_sigma=0.005):
-    """Seeded hypotheses generated ON the device (config 5 is 52 M poses; host generation
-    would dominate).  Same distributions as workloads.random_poses."""
-    g = torch.Generator(device=device)
-    g.manual_seed(int(seed))
-    gq = torch.nn.functional.normalize(torch.randn(n, 4, generator=g, device=device), dim=1)
-    pq = torch.nn.functional.normalize(gq + rot_sigma * torch.randn(n, 4, generator=g, device=device), dim=1)
-    u = torch.rand(n, 3, generator=g, device=device)
-    gt = torch.stack([u[:, 0] * 0.4 - 0.2, u[:, 1] * 0.4 - 0.2, u[:, 2] * 0.8 + 0.4], 1)
-    pt = gt + trans_sigma * torch.randn(n, 3, generator=g, device=device)
-    return pq, pt, gq, gt
+VARIANT_KINDS = {"rgb": 0, "rgbd": 0, "rgb_geometric": 1, "rgbd_geometric": 2}
 
 
-def variant_translation(variant: str, pred_t, gt_t, K, seed: int):
-    """How each model family produces its translation:
-    rgb / rgbd regress xyz directly; rgb_geometric predicts Z and back-projects the bbox
-    centre (kernel d1); rgbd_geometric reads Z from a depth crop under the crop-space
-    centre (kernel d2)."""
-    from .utils.camera import depth_backproject, pinhole_translation
-    if variant in ("rgb", "rgbd"):
-        return pred_t
-    dev = pred_t.device
-    fx, fy, cx, cy = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
-    uv = torch.stack([gt_t[:, 0] / gt_t[:, 2] * fx + cx, gt_t[:, 1] / gt_t[:, 2] * fy + cy], 1)
-    if variant == "rgb_geometric":
-        return pinhole_translation(pred_t[:, 2:3].contiguous(), uv, K)
-    if variant == "rgbd_geometric":
-        # a tiny synthetic "crop": 8x8 depth patch around the centre, noisy sensor depth of the GT
-        n = pred_t.shape[0]
-        g = torch.Generator(device=dev); g.manual_seed(int(seed) + 7)
-        depth = gt_t[:, 2].reshape(n, 1, 1) + 0.002 * torch.randn(n, 8, 8, generator=g, device=dev)
-        centre = torch.full((n, 2), 3.5, device=dev)
-        Kc = K.clone().reshape(1, 3, 3).repeat(n, 1, 1)
-        Kc[:, 0, 2] = 3.5 - (uv[:, 0] - cx)          # crop-space principal point so that (u-cx) is preserved
-        Kc[:, 1, 2] = 3.5 - (uv[:, 1] - cy)
-        return depth_backproject(depth.contiguous(), centre, Kc, clamp_hi=7.0)
-    raise ValueError(f"unknown variant {variant!r}")
-
-
-def evaluate_sweep(points: dict, diameters: dict, device, n_per_block: int, variants=VARIANTS, chunk: int = 65536,
-                   seed: int = 5000, rank: int = 0, world: int = 1, group=None, K=None):
-    """compare_all_models-style sweep: for every (object, variant) block, `n_per_block`
-    seeded hypotheses, the hypothesis axis of each block sliced across `world` ranks.
-    Returns (Accumulators after the all-reduce, number of kernel launches on this rank)."""
+def synth_block(n: int, first: int, seed: int, obj_index: int, variant_index: int, variant: str, oid: int, device,
+                K=None, rot_sigma=0.05, trans_sigma=0.005) -> dict:
+    """Hypotheses [first, first + n) of block (obj_index, variant_index) as the native sweep generates
+    them (p6d_synth_poses: counter-based, a pure function of seed / block / hypothesis index), plus
+    the variant's raw translation inputs: ``pt`` (kind 0), ``z``/``uv`` (kind 1) or
+    ``uv``/``kc``/``depth`` (kind 2).  For tests and for callers that want the data itself."""
     dev = core.require_cuda(device)
-    ev = PoseEvaluator(points, diameters, dev, n_rows=len(variants))
+    kind = VARIANT_KINDS[variant]
     if K is None:
         from .utils.camera import DEFAULT_K
-        K = torch.tensor(DEFAULT_K, dtype=torch.float32, device=dev)
-    objs = sorted(points)
+        K = DEFAULT_K
+    Kh = np.ascontiguousarray(np.asarray(K, np.float32).reshape(9))
+    f32 = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+    out = {"pq": f32(n, 4), "gq": f32(n, 4), "gt": f32(n, 3), "obj": torch.empty(n, dtype=torch.int64, device=dev)}
+    if kind == 0:
+        out["pt"] = f32(n, 3)
+    elif kind == 1:
+        out["z"], out["uv"] = f32(n), f32(n, 2)
+    else:
+        out["uv"], out["kc"], out["depth"] = f32(n, 2), f32(n, 3, 3), f32(n, 8, 8)
+    g = lambda k: core.ptr(out.get(k))
+    core.check(core.lib().p6d_synth_poses(int(seed), int(obj_index), int(variant_index), int(first), int(n),
+                                          float(rot_sigma), float(trans_sigma), kind, core.ptr(Kh), int(oid),
+                                          g("pq"), g("pt"), g("gq"), g("gt"), g("obj"), g("z"), g("uv"), g("kc"),
+                                          g("depth"), dev.index, core.stream_ptr(dev)))
+    return out
+
+
+def variant_translation(variant: str, block: dict, K):
+    """How each model family produces its translation, from the
+    raw inputs of ``synth_block``: rgb / rgbd regress xyz directly; rgb_geometric predicts Z and
+    back-projects the bbox centre (kernel d1, reference models/pose_net_rgb_geometric.py:93-109);
+    rgbd_geometric reads Z from a depth crop under the crop-space centre (kernel d2, reference
+    models/pose_net_rgbd_geometric.py:56-85)."""
+    from .utils.camera import depth_backproject, pinhole_translation
+    kind = VARIANT_KINDS[variant]
+    if kind == 0:
+        return block["pt"]
+    if kind == 1:
+        return pinhole_translation(block["z"].reshape(-1, 1), block["uv"], K)
+    return depth_backproject(block["depth"], block["uv"], block["kc"], clamp_hi=7.0)
+
+
+def evaluate_sweep(points: dict, diameters: dict, device, n_per_block: int, variants=VARIANTS, chunk: int = 262144,
+                   seed: int = 5000, rank: int = 0, world: int = 1, group=None, K=None, check_n: int = 0,
+                   rot_sigma: float = 0.05, trans_sigma: float = 0.005, evaluator: "PoseEvaluator | None" = None):
+    """compare_all_models-style sweep (reference scripts/visualization/compare_all_models.py:65-104 at the
+    scale of BASELINE config 5): for every (object, variant) block, `n_per_block` seeded hypotheses, the
+    hypothesis axis of each block sliced across `world` ranks (`shard_range`).  The whole sweep of this
+    rank is ONE native call (p6d_sweep_run: generation, the variant's translation kernel and the
+    evaluation overlap on two streams); the only collective is the all-reduce of the accumulators at
+    the end.  Returns (Accumulators after the all-reduce, kernel launches on this rank, check) where
+    `check` holds the first `check_n` hypotheses of every block of this rank's slice exactly as they
+    were evaluated (inputs and outputs, host arrays) for an independent re-evaluation, or None."""
+    dev = core.require_cuda(device)
+    ev = evaluator or PoseEvaluator(points, diameters, dev, n_rows=len(variants))
+    if K is None:
+        from .utils.camera import DEFAULT_K
+        K = DEFAULT_K
+    Kh = np.ascontiguousarray((K.detach().cpu().numpy() if isinstance(K, torch.Tensor) else np.asarray(K))
+                              .astype(np.float32).reshape(9))
+    objs = np.ascontiguousarray(sorted(int(o) for o in points), dtype=np.int32)
+    kinds = np.ascontiguousarray([VARIANT_KINDS[v] for v in variants], dtype=np.int32)
     lo, hi = shard_range(n_per_block, rank, world)
-    for oi, oid in enumerate(objs):
-        for vi, var in enumerate(variants):
-            # chunks live on a global grid and are seeded by their global index, so the data
-            # (and therefore every count) is the same for any number of ranks
-            for c in range(lo // chunk, (hi + chunk - 1) // chunk):
-                c0 = c * chunk
-                n = min(chunk, n_per_block - c0)
-                cseed = seed + 1_000_003 * oi + 10_007 * vi + c
-                pq, pt, gq, gt = synth_chunk(n, cseed, dev)
-                pt = variant_translation(var, pt, gt, K, cseed)
-                a, b = max(lo, c0) - c0, min(hi, c0 + n) - c0
-                if b <= a:
-                    continue
-                obj = torch.full((b - a,), oid, dtype=torch.int64, device=dev)
-                ev.evaluate(pq[a:b], pt[a:b], gq[a:b], gt[a:b], obj, row=vi, sort=False)
+    cn = min(int(check_n), hi - lo)
+    nb = len(objs) * len(variants)
+    check = None
+    if cn > 0:
+        check = {"pq": np.empty((nb, cn, 4), np.float32), "pt": np.empty((nb, cn, 3), np.float32),
+                 "gq": np.empty((nb, cn, 4), np.float32), "gt": np.empty((nb, cn, 3), np.float32),
+                 "add": np.empty((nb, cn), np.float32), "adds": np.empty((nb, cn), np.float32),
+                 "hit": np.empty((nb, cn), np.uint8),
+                 "obj": np.repeat(objs.astype(np.int64), len(variants))[:, None].repeat(cn, 1),
+                 "variant": np.tile(np.arange(len(variants)), len(objs)), "first": lo}
+    launches = C.c_int(0)
+    cp = lambda k: core.ptr(check[k]) if check is not None else None
+    acc = ev.acc
+    core.check(core.lib().p6d_sweep_run(ev.table.handle, core.ptr(objs), len(objs), core.ptr(kinds), len(variants),
+                                        int(n_per_block), int(lo), int(hi), int(chunk), int(seed), core.ptr(Kh),
+                                        float(rot_sigma), float(trans_sigma), core.ptr(acc.hits), core.ptr(acc.valid),
+                                        core.ptr(acc.add_sum), core.ptr(acc.adds_sum), cn, cp("pq"), cp("pt"), cp("gq"),
+                                        cp("gt"), cp("add"), cp("adds"), cp("hit"), C.byref(launches),
+                                        core.stream_ptr(dev)))
+    ev.launches += launches.value
     ev.all_reduce(group)
-    return ev.acc, ev.launches
+    return ev.acc, launches.value, check

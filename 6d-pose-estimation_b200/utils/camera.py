@@ -7,24 +7,17 @@ in two model methods (``models/pose_net_rgb_geometric.py:93-109`` and
 ``models/pose_net_rgbd_geometric.py:56-85``); those methods can delegate here one-to-one
 (INTEGRATION.md).  CUDA only, no CPU path.
 """
-import importlib.util
 import os
-import sys
 
 import numpy as np
 import torch
 import yaml
 
 
-def _core():
-    mod = sys.modules.get("p6d_b200_core")
-    if mod is None:
-        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        spec = importlib.util.spec_from_file_location("p6d_b200_bootstrap", os.path.join(here, "_bootstrap.py"))
-        boot = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(boot)
-        mod = boot.core()
-    return mod
+try:                                    # imported as part of the package ...
+    from .._p6d_bootstrap import core as _core
+except ImportError:                     # ... or as top-level `models` / `utils` (drop-in layout: this
+    from _p6d_bootstrap import core as _core   # directory is at the front of sys.path, see dropin.py)
 
 
 # LineMOD intrinsics used when a frame has none (reference utils/camera.py:8-12)

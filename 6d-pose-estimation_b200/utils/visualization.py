@@ -6,24 +6,15 @@ float64 like the reference).  ``project_points_batch`` is an addition: the same 
 for B poses at once on the GPU (float64 kernel ``p6d_project_points``), e.g. the 8 box
 corners of every hypothesis of a sweep.
 """
-import importlib.util
-import os
-import sys
-
 import numpy as np
 
 _EDGES = ((0, 1), (1, 2), (2, 3), (3, 0), (4, 5), (5, 6), (6, 7), (7, 4), (0, 4), (1, 5), (2, 6), (3, 7))
 
 
-def _core():
-    mod = sys.modules.get("p6d_b200_core")
-    if mod is None:
-        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        spec = importlib.util.spec_from_file_location("p6d_b200_bootstrap", os.path.join(here, "_bootstrap.py"))
-        boot = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(boot)
-        mod = boot.core()
-    return mod
+try:                                    # imported as part of the package ...
+    from .._p6d_bootstrap import core as _core
+except ImportError:                     # ... or as top-level `utils` (drop-in layout, see dropin.py)
+    from _p6d_bootstrap import core as _core
 
 
 def _rotation_matrix(rotation):

@@ -36,7 +36,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define P6D_VERSION 1
+#define P6D_VERSION 2
 
 #define P6D_OK 0
 #define P6D_EINVAL (-1)   /* bad argument */
@@ -72,9 +72,24 @@ int p6d_mesh_table_destroy(p6d_mesh_table* table);
 /* Largest mesh (points) the ADD-S kernel accepts on this device. */
 int p6d_adds_max_points(int device, int* max_points);
 
-/* 1 if the build's post-link pass (csrc/sass_sched.py) re-laid the ADD-S scan loop, 0 if the
- * library runs ptxas' own schedule (same results, about 4 % slower at 2,048 points). */
+/* The build's post-link pass (csrc/sass_sched.py) re-lays the scan loop of the ADD-S kernels (same
+ * instructions, other order and stall counts; +4...9 % throughput).  Before a re-laid kernel is
+ * used on a device, the library runs it and the ptxas-scheduled kernel of the same mesh-size class
+ * on 592 seeded poses and compares every output byte; on any difference it prints one line to
+ * stderr and uses the ptxas-scheduled kernel for the rest of the process.  The environment
+ * variable P6D_ADDS_SCHEDULE=ptxas turns the re-laid kernels off altogether.
+ *   p6d_adds_schedule()        1 if re-laid kernels are in the build and none has been rejected
+ *   p6d_adds_schedule_state()  for the table's class: built_relaid 0/1; runtime_state 0 = not yet
+ *                              checked, 1 = verified on this device, 2 = rejected
+ *   p6d_adds_selfcheck()       runs the comparison now on n_poses seeded poses over the table's
+ *                              meshes; mismatches = differing output bytes (0 when nothing is re-laid) */
 int p6d_adds_schedule(void);
+int p6d_adds_schedule_state(const p6d_mesh_table* table, int* built_relaid, int* runtime_state);
+int p6d_adds_selfcheck(const p6d_mesh_table* table, int64_t n_poses, int64_t* mismatches);
+
+/* All 2^32 float32 bit patterns through the packed square root of kernel (a) and through
+ * sqrt.rn.f32; mismatches must come back 0. */
+int p6d_selftest_sqrt2(int device, int64_t* mismatches);
 
 /* ---------------------------------------------------------------------------------------
  * Per-pose evaluation = the loop body of ADDLoss.eval_metrics (models/add_loss.py:168-195)
@@ -87,6 +102,10 @@ int p6d_adds_schedule(void);
  *                all-pairs part (ADD-only kernel, symmetric ids then decide on ADD)
  *   hit  [B]     (double)(symmetric ? adds : add) < 0.1*diameter  (:192-195)
  *   valid[B]     0 where the object id has no mesh (outputs 0 there)
+ *   borderline   nullable [B]: 1 where the deciding distance lies within 4 float32 ulp of the
+ *                threshold -- the band in which a reference running on another
+ *                BLAS / ATen build could round to the other side; callers that need certainty
+ *                against such a build re-evaluate exactly these poses with it
  *   acc          nullable per-object accumulators updated with atomics (not zeroed here):
  *                hits[n_slots], valid[n_slots] int64; add_sum[n_slots], adds_sum[n_slots]
  *                float64 (any of the four pointers may be NULL)
@@ -102,8 +121,8 @@ typedef struct p6d_accumulators {
 
 int p6d_add_eval(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
                  const float* gt, const int64_t* obj, const int32_t* order, int64_t B, float* add,
-                 float* adds, uint8_t* hit, uint8_t* valid, const p6d_accumulators* acc,
-                 void* stream);
+                 float* adds, uint8_t* hit, uint8_t* valid, uint8_t* borderline,
+                 const p6d_accumulators* acc, void* stream);
 
 /* Same computation with HOST buffers: stages inputs to the device, runs the kernels,
  * copies results back and synchronises (the end-to-end path of bench.py).  acc_* are
@@ -111,20 +130,39 @@ int p6d_add_eval(const p6d_mesh_table* table, const float* pq, const float* pt, 
  * gpu_launches (nullable) receives the number of kernels this call launched. */
 int p6d_add_eval_host(p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
                       const float* gt, const int64_t* obj, int64_t B, int want_adds, float* add,
-                      float* adds, uint8_t* hit, uint8_t* valid, int64_t* acc_hits,
-                      int64_t* acc_valid, double* acc_add_sum, double* acc_adds_sum,
+                      float* adds, uint8_t* hit, uint8_t* valid, uint8_t* borderline,
+                      int64_t* acc_hits, int64_t* acc_valid, double* acc_add_sum, double* acc_adds_sum,
                       int* gpu_launches);
+
+/* ---------------------------------------------------------------------------------------
+ * Value of ADDLoss.forward (models/add_loss.py:101-150) in ONE launch and no host
+ * synchronisation: per sample ADD (asymmetric ids) or ADD-S (symmetric ids) with the rounding
+ * of the reference's batched torch.matmul, then -- by the last CTA to finish -- the reference's
+ * grouping: objects in order of first appearance, per object the float32 sum of its samples
+ * (ATen order), added to the running total; total / count.
+ *   loss  [1] device float32 (0 when no sample has a mesh); count [1] device int32
+ *   workspace: device buffer of p6d_add_forward_workspace_bytes(table, B) bytes, 16-byte aligned
+ * Bit-exact against the reference for meshes of up to 44 points (ATen's naive bmm kernel) and
+ * from 45 points on (MKL, fused chain), except group sizes for which MKL's batched sgemm takes
+ * another path (observed: exactly 2 samples of a 97...106- or 200-point mesh): 1e-5 there.
+ * ------------------------------------------------------------------------------------- */
+int64_t p6d_add_forward_workspace_bytes(const p6d_mesh_table* table, int64_t B);
+int p6d_add_forward(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                    const float* gt, const int64_t* obj, int64_t B, float* loss, int32_t* count,
+                    void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Gradient of ADDLoss.forward (models/add_loss.py:101-150) w.r.t. pred_r [B,4] and
  * pred_t [B,3]:  loss = (1/count) * sum over valid samples of ADD (asymmetric ids) or
  * ADD-S (symmetric ids).  grad_out: device pointer to the upstream scalar gradient;
- * inv_count = 1 / number of valid samples.  Skipped samples get zero gradient.
+ * count: device pointer to the number of valid samples (as written by p6d_add_forward), or
+ * NULL to use the host value inv_count = 1 / count.  Skipped samples get zero gradient.
  * ------------------------------------------------------------------------------------- */
 int p6d_add_backward(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
                      const float* gt, const int64_t* obj, int64_t B, const float* grad_out,
-                     float inv_count, float* grad_q, float* grad_t, void* stream);
+                     const int32_t* count, float inv_count, float* grad_q, float* grad_t, void* stream);
 
+#ifdef P6D_DEV   /* development build only (make -C csrc dev) */
 /* Measurement helper: runs the ADD-S kernel once (device buffers, legacy stream, synchronous)
  * and returns, per CTA, {smid, globaltimer start, globaltimer end, poses processed} so the
  * load balance of the persistent grid can be inspected.  timeline_host holds 4*max_ctas
@@ -133,6 +171,7 @@ int p6d_adds_timeline(const p6d_mesh_table* table, const float* pq, const float*
                       const float* gt, const int64_t* obj, const int32_t* order, int64_t B, float* add,
                       float* adds, uint8_t* hit, uint8_t* valid, uint64_t* timeline_host, int max_ctas,
                       int* n_ctas);
+#endif
 
 /* Quaternion -> rotation matrix, ADDLoss._quat_to_mat (models/add_loss.py:203-215). */
 int p6d_quat_to_mat(const float* q, int64_t B, float* R, int device, void* stream);
@@ -201,6 +240,49 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
  * integers; uv [B,N,2] int64. */
 int p6d_project_points(const double* points, int N, const double* rotation, int rotation_is_quat,
                        const double* translation, const double* K, int64_t B, int64_t* uv, int device, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The compare_all_models sweep (scripts/visualization/compare_all_models.py:65-104 at the scale
+ * of BASELINE config 5) for one rank, driven natively on two streams.
+ *   p6d_synth_poses  seeded pose hypotheses generated on the device; a pure function of
+ *                    (seed, obj_index, variant_index, first + i), so any sharding sees the same data.
+ *                    kind 0: pred_t direct (RGB / RGBD heads) -> pt
+ *                    kind 1: RGB-Geometric inputs z [n], uv [n,2] (bbox centre) for p6d_pinhole_fwd
+ *                    kind 2: RGBD-Geometric inputs uv [n,2] (crop centre), kc [n,9], depth [n,8,8]
+ *                            for p6d_depth_backproject(H = W = 8, clamp_hi = 7)
+ *   p6d_sweep_run    for every (object, variant) block the hypotheses [lo, hi) of n_per_block, in
+ *                    chunks: generate, translate (kernel d1 / d2 by variant kind), evaluate
+ *                    (ADD + ADD-S + decision) into the variant's accumulator row.
+ *                    acc_* : device [n_variants, n_slots], accumulated with atomics (not zeroed);
+ *                    check_*: host arrays [n_obj * n_variants * min(check_n, hi - lo), ...] receiving
+ *                    the first poses of every block as evaluated (inputs and outputs) so the caller
+ *                    can re-evaluate them independently; nullable when check_n = 0.
+ *                    Work is ordered after what is already queued on `stream`; the call returns
+ *                    after the sweep has finished.
+ * ------------------------------------------------------------------------------------- */
+int p6d_synth_poses(uint64_t seed, int obj_index, int variant_index, int64_t first, int64_t n,
+                    float rot_sigma, float trans_sigma, int kind, const float* K_host, int64_t oid,
+                    float* pq, float* pt, float* gq, float* gt, int64_t* obj, float* z, float* uv,
+                    float* kc, float* depth, int device, void* stream);
+int p6d_sweep_run(p6d_mesh_table* table, const int32_t* obj_ids, int n_obj, const int32_t* variant_kinds,
+                  int n_variants, int64_t n_per_block, int64_t lo, int64_t hi, int64_t chunk, uint64_t seed,
+                  const float* K_host, float rot_sigma, float trans_sigma, int64_t* acc_hits,
+                  int64_t* acc_valid, double* acc_add_sum, double* acc_adds_sum, int64_t check_n,
+                  float* check_pq, float* check_pt, float* check_gq, float* check_gt, float* check_add,
+                  float* check_adds, uint8_t* check_hit, int* gpu_launches, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * OPT-IN EVIDENCE KERNEL, not used by any product path: ADD-S (models/add_loss.py:185-190) in GEMM
+ * form, d^2 = |p|^2 + |g|^2 - 2 p.g, on the tcgen05 tensor cores (kind::tf32, FP32 accumulators in
+ * TMEM); split_terms = 3: error-compensated 3xTF32 operands, 1: plain TF32.  BASELINE.json's
+ * north_star excludes tensor cores from the ADD-S kernel "unless a 3xTF32 variant passes the stated
+ * tolerance" (1e-5 relative); tests/test_tf32_variant.py measures this kernel against the oracle.
+ *   adds [B] device float32: mean_i min_j |pred_i - gt_j| as this formulation computes it
+ *   max_ctas: 0 = one CTA per SM.  Synchronises the stream before returning.
+ * ------------------------------------------------------------------------------------- */
+int p6d_adds_tf32_eval(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                       const float* gt, const int64_t* obj, int64_t B, int split_terms, float* adds,
+                       int max_ctas, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Measurement helper (no reference counterpart): FP32 issue-rate microbenchmarks that give

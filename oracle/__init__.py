@@ -134,8 +134,10 @@ class MeshTable:
         self.xyz = np.concatenate(chunks, 0) if chunks else np.zeros((1, 3), np.float32)
 
 
-def add_eval(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids, want_adds=True, n_threads=1):
-    """Per-pose ADD, ADD-S, ADD-0.1d hit and validity (models/add_loss.py:168-195)."""
+def add_eval(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids, want_adds=True, n_threads=1, bmm=False):
+    """Per-pose ADD, ADD-S, ADD-0.1d hit and validity (models/add_loss.py:168-195).
+    bmm=True: clouds transformed with the rounding of the batched torch.matmul of
+    ``ADDLoss.forward`` (models/add_loss.py:132-133) instead of torch.mm's."""
     pq, pt, gq, gt = (_f32(pred_q).reshape(-1, 4), _f32(pred_t).reshape(-1, 3),
                       _f32(gt_q).reshape(-1, 4), _f32(gt_t).reshape(-1, 3))
     obj = np.ascontiguousarray(obj_ids, dtype=np.int64).ravel()
@@ -148,7 +150,7 @@ def add_eval(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids, want_adds=Tr
         _ptr(table.xyz, C.c_float), _ptr(table.offsets, C.c_int32), _ptr(table.counts, C.c_int32),
         _ptr(table.diameters, C.c_double), _ptr(table.symmetric, C.c_uint8), table.n_slots,
         _ptr(pq, C.c_float), _ptr(pt, C.c_float), _ptr(gq, C.c_float), _ptr(gt, C.c_float),
-        _ptr(obj, C.c_int64), B, 1 if want_adds else 0, _ptr(add, C.c_float), _ptr(adds, C.c_float),
+        _ptr(obj, C.c_int64), B, (1 if want_adds else 0) | (2 if bmm else 0), _ptr(add, C.c_float), _ptr(adds, C.c_float),
         _ptr(hit, C.c_uint8), _ptr(valid, C.c_uint8), int(n_threads))
     if rc != 0:
         raise MemoryError("oracle add_eval failed")
@@ -173,7 +175,7 @@ def add_forward(table: MeshTable, pred_q, pred_t, gt_q, gt_t, obj_ids) -> np.flo
     """Value of ``ADDLoss.forward`` (models/add_loss.py:101-150): per object group, the
     float32 ATen sum of the per-sample ADD (or ADD-S for symmetric ids), accumulated in
     first-appearance order, divided by the number of valid samples."""
-    add, adds, _, valid = add_eval(table, pred_q, pred_t, gt_q, gt_t, obj_ids, True)
+    add, adds, _, valid = add_eval(table, pred_q, pred_t, gt_q, gt_t, obj_ids, True, bmm=True)
     obj = np.asarray(obj_ids, np.int64).ravel()
     order, groups = [], {}
     for i, o in enumerate(obj):

@@ -160,6 +160,28 @@ def gen_forward():
          dia=np.array([dia[i] for i in sorted(dia)], np.float64), **pack_points(pts))
 
 
+def gen_forward_more():
+    """Further ADDLoss.forward values (no grads): the reference's default mesh size, tiny meshes
+    (torch.matmul's naive kernel rounds differently from MKL for n <= 44) and a mixed batch."""
+    def one(name, pts, dia, B, seed, ids):
+        crit = make_crit(pts, dia)
+        pq, pt, gq, gt = W.random_poses(B, seed, rot_sigma=np.geomspace(0.01, 0.2, B), trans_sigma=0.01)
+        obj = np.asarray(ids, np.int64)[np.random.RandomState(seed + 1).randint(0, len(ids), B)]
+        with torch.no_grad():
+            loss = crit(T(pq), T(pt), T(gq), T(gt), T(obj))
+        save(name, pq=pq, pt=pt, gq=gq, gt=gt, obj=obj, loss=np.float32(loss.item()),
+             dia_ids=np.array(sorted(dia), np.int64), dia=np.array([dia[i] for i in sorted(dia)], np.float64),
+             **pack_points(pts))
+    pts, dia = W.sweep_meshes(500)
+    one("add_forward_n500", pts, dia, 32, 81, W.LINEMOD_IDS)
+    small = {0: W.sphere_mesh(1, 0.1, 82), 1: W.sphere_mesh(2, 0.1, 83), 3: W.sphere_mesh(10, 0.1, 84),
+             4: W.sphere_mesh(11, 0.1, 85), 9: W.box_mesh(44, (0.1, 0.12, 0.05), 86), 10: W.box_mesh(33, (0.04, 0.17, 0.04), 87)}
+    one("add_forward_small", small, {k: 0.1 for k in small}, 48, 88, sorted(small))
+    mixed = {0: W.sphere_mesh(44, 0.1, 89), 1: W.sphere_mesh(45, 0.1, 90), 9: W.box_mesh(300, (0.1, 0.12, 0.05), 91),
+             10: W.box_mesh(1000, (0.04, 0.17, 0.04), 92), 12: W.sphere_mesh(640, 0.2, 93)}
+    one("add_forward_mixed", mixed, {k: 0.15 for k in mixed}, 40, 94, sorted(mixed) + [6, 7])
+
+
 def gen_pose_loss():
     c = W.config3(32, 3)
     net = PoseNetRGBGeometric.__new__(PoseNetRGBGeometric)  # stateless method, no ResNet build
@@ -333,7 +355,7 @@ def gen_projection():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_quat(); gen_eval(); gen_forward(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_projection()
+    gen_quat(); gen_eval(); gen_forward(); gen_forward_more(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_projection()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/gen_golden.py from {REF}\n"
                 f"torch {torch.__version__} cpu_capability {torch.backends.cpu.get_cpu_capability()} "

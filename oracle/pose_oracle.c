@@ -159,7 +159,13 @@ P6O_API void p6o_quat_to_mat(const float* q, float* R) {
  * torch.mm's float32 rounding depends on the row count n of the [n,3] x [3,3] product
  * (measured, torch 2.11.0 + MKL 2024.2): n >= 11 takes the k-sequential FMA chain;
  * tiny products take unfused kernels: n == 1 -> (p1*r1 + p2*r2) + p0*r0,
- * 2 <= n <= 10 -> (p0*r0 + p2*r2) + p1*r1. */
+ * 2 <= n <= 10 -> (p0*r0 + p2*r2) + p1*r1.
+ * The loss form (models/add_loss.py:132-133) goes through torch.matmul on a [1,n,3] x [B,3,3]
+ * batch instead (measured, same build): ATen's naive bmm kernel for 3*n*3 < 400, i.e. n <= 44,
+ * which accumulates left to right without fusing, and the FMA chain above that (except where MKL's
+ * batched sgemm takes another path: observed for exactly 2 samples of a 97..106- or 200-point mesh).
+ * Callers select that rule by passing n = P6O_BMM(n). */
+#define P6O_BMM(n) ((n) <= 44 ? (int64_t)-1 : (int64_t)11)
 static inline void p6o_xform_point(const float* m, const float* R, const float* t, int64_t n,
                                    float* o) {
     for (int c = 0; c < 3; ++c) {
@@ -169,6 +175,8 @@ static inline void p6o_xform_point(const float* m, const float* R, const float* 
             v = m[0] * r[0];
             v = fmaf(m[1], r[1], v);
             v = fmaf(m[2], r[2], v);
+        } else if (n < 0) {
+            v = (m[0] * r[0] + m[1] * r[1]) + m[2] * r[2];
         } else if (n == 1) {
             v = (m[1] * r[1] + m[2] * r[2]) + m[0] * r[0];
         } else {
@@ -204,7 +212,8 @@ static inline float p6o_min_nan(float a, float b) {
  * ---------------------------------------------------------------------------------- */
 static void p6o_pose_distances(const float* mesh, int64_t n, const float* pq, const float* pt,
                                const float* gq, const float* gt, int want_adds, float* add_out,
-                               float* adds_out, float* scratch) {
+                               float* adds_out, float* scratch, int bmm) {
+    const int64_t rule = bmm ? P6O_BMM(n) : n;
     float Rp[9], Rg[9];
     p6o_quat_to_mat(pq, Rp);
     p6o_quat_to_mat(gq, Rg);
@@ -213,8 +222,8 @@ static void p6o_pose_distances(const float* mesh, int64_t n, const float* pq, co
     float* d = gz + n;
     for (int64_t i = 0; i < n; ++i) {
         float p[3], g[3];
-        p6o_xform_point(mesh + 3 * i, Rp, pt, n, p);
-        p6o_xform_point(mesh + 3 * i, Rg, gt, n, g);
+        p6o_xform_point(mesh + 3 * i, Rp, pt, rule, p);
+        p6o_xform_point(mesh + 3 * i, Rg, gt, rule, g);
         px[i] = p[0]; py[i] = p[1]; pz[i] = p[2];
         gx[i] = g[0]; gy[i] = g[1]; gz[i] = g[2];
         d[i] = sqrtf(p6o_sq3(p[0] - g[0], p[1] - g[1], p[2] - g[2]));
@@ -245,8 +254,9 @@ static void p6o_pose_distances(const float* mesh, int64_t n, const float* pq, co
  *   diameters[n_slots] (metres, float64); threshold = 0.1 * diameter in float64 (:176)
  *   symmetric[n_slots] : 1 for ids in SYMMETRIC_OBJECT_IDS (:10,:193-194)
  * Outputs per pose: add, adds (float32, 0 when skipped), hit, valid (uint8).
- * want_adds = 0 skips the N^2 part (adds untouched; symmetric ids then decide on ADD,
- * which the reference never does -- only used by the ADD-only kernel's tests).
+ * want_adds bit 0 clear skips the N^2 part (adds untouched; symmetric ids then decide on ADD,
+ * which the reference never does -- only used by the ADD-only kernel's tests); bit 1 set
+ * transforms with torch.matmul's rounding (the loss form, ADDLoss.forward).
  * ---------------------------------------------------------------------------------- */
 typedef struct {
     const float* mesh_xyz; const int32_t* offsets; const int32_t* counts;
@@ -272,10 +282,11 @@ static void* p6o_eval_worker(void* arg) {
             J->valid[b] = 0;
             continue;
         }
-        const int do_s = J->want_adds && J->adds != NULL;
+        const int do_s = (J->want_adds & 1) && J->adds != NULL;
         float a = 0.0f, as = 0.0f;
         p6o_pose_distances(J->mesh_xyz + 3 * (int64_t)J->offsets[oid], J->counts[oid], J->pq + 4 * b,
-                           J->pt + 3 * b, J->gq + 4 * b, J->gt + 3 * b, do_s, &a, &as, scratch);
+                           J->pt + 3 * b, J->gq + 4 * b, J->gt + 3 * b, do_s, &a, &as, scratch,
+                           (J->want_adds & 2) != 0);
         J->add[b] = a;
         if (do_s) J->adds[b] = as;
         const double thr = 0.1 * J->diameters[oid];
@@ -343,11 +354,11 @@ P6O_API int p6o_add_backward(const float* mesh_xyz, const int32_t* offsets, cons
         float Rp[9], Rg[9];
         p6o_quat_to_mat(pq + 4 * b, Rp);
         p6o_quat_to_mat(gq + 4 * b, Rg);
-        for (int64_t i = 0; i < n; ++i) p6o_xform_point(mesh + 3 * i, Rg, gt + 3 * b, n, g + 3 * i);
+        for (int64_t i = 0; i < n; ++i) p6o_xform_point(mesh + 3 * i, Rg, gt + 3 * b, P6O_BMM(n), g + 3 * i);
         double T[3] = {0, 0, 0}, R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int64_t i = 0; i < n; ++i) {
             float p[3];
-            p6o_xform_point(mesh + 3 * i, Rp, pt + 3 * b, n, p);
+            p6o_xform_point(mesh + 3 * i, Rp, pt + 3 * b, P6O_BMM(n), p);
             int64_t js = i;
             if (symmetric[oid]) {
                 float best = INFINITY;
