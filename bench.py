@@ -8,14 +8,26 @@ by the NCCL all-reduce of the per-object hit counts.  Weak scaling: every rank e
 its own 65,536 hypotheses; `value` is the whole-job rate.
 
   python bench.py [--gpus N --steps K --warmup W]        our arm (one process per GPU)
-  python bench.py --impl reference [...]                 CPU arm: the oracle port of the
-        reference's algorithm on all host cores, same metric, bounded sample per step
+  python bench.py --impl reference [...]                 CPU arm: the UNMODIFIED reference
+        (baseline/_ref, P6D_REFERENCE or /root/reference: ADDLoss.eval_metrics in batches of 16 on
+        all host cores) when it is reachable, else the oracle port of its algorithm; same metric,
+        bounded sample per step
+
+Beside the headline the line carries
+  `sweep`      BASELINE config 5 (13 objects x 4 variants x 1 M hypotheses, 500- and 2,048-point
+               meshes) as a STRONG-scaling record: fixed total work sliced over the ranks, seconds
+               (max over ranks), per-variant integer hit totals (identical for every N) and an
+               oracle check of the first poses of every block;
+  `secondary`  the other kernels of the path against their own bounds;
+  `cpu_baseline` the reference itself (when reachable) and the oracle port on the host cores,
+               with the reference's per-pose decisions compared to the GPU's.
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the roofline arithmetic.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import importlib
 import json
 import os
@@ -36,6 +48,8 @@ FLOP_PER_POSE = 8 * N_POINTS * N_POINTS            # 3 sub + 3 mul + 2 add per p
 BYTES_PER_POSE = 64 + 10                            # 14 floats + int64 id in, 2 floats + 2 bytes out
 METRIC = "ADD-S pose evals/sec (2k-pt mesh)"
 UNIT = "poses/s"
+SWEEP_SEED = 5000
+REF_BATCH = 16                                      # compare_all_models.py:121,125
 
 
 def parse():
@@ -46,10 +60,14 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--poses", type=int, default=POSES_PER_GPU, help="hypotheses per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0,
-                    help="poses timed on the CPU baseline (0 = sized for ~12 s of CPU work)")
+                    help="poses timed on the CPU port baseline (0 = sized for ~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-microbench", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the HBM-bound secondary kernels")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary kernels")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 sweep record")
+    ap.add_argument("--sweep-per-block", type=int, default=1_000_000, help="hypotheses per (object, variant) block")
+    ap.add_argument("--sweep-points", default="500,2048", help="mesh sizes of the sweep record")
+    ap.add_argument("--sweep-check", type=int, default=256, help="poses per block checked against the oracle")
     return ap.parse_args()
 
 
@@ -142,7 +160,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ------------------------------------------------------------------------- CPU arm
+# ------------------------------------------------------------------------- CPU arms
 def cpu_rate(W, n_poses, threads=None):
     """Oracle port of the reference algorithm on the host cores (bounded sample)."""
     import oracle as O
@@ -158,46 +176,143 @@ def cpu_rate(W, n_poses, threads=None):
     return n_poses / dt, threads, dt
 
 
+def real_reference():
+    """(root, criterion of the UNMODIFIED reference on the CPU with the config-2 meshes) or (None, why)."""
+    try:
+        from oracle import torch_eager as E
+        root = E.find_reference()
+        if root is None:
+            return None, "no reference checkout (P6D_REFERENCE, baseline/_ref, /root/reference)"
+        W = importlib.import_module("6d-pose-estimation_b200.workloads")
+        pts, dia = W.config2_meshes(N_POINTS)
+        return root, E.reference_criterion(root, pts, dia)
+    except Exception as e:  # an import error of the reference must not take the bench line down
+        return None, f"reference not importable: {e!r}"
+
+
+def reference_eval_batches(crit, poses, lo, hi):
+    """The reference's own call pattern (scripts/visualization/compare_all_models.py:95): eval_metrics on
+    batches of 16.  Returns the list of result dicts."""
+    import torch
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    pq, pt, gq, gt, obj = poses
+    out = []
+    for b in range(lo, hi, REF_BATCH):
+        e = min(hi, b + REF_BATCH)
+        out.append(crit.eval_metrics(T(pq[b:e]), T(pt[b:e]), T(gq[b:e]), T(gt[b:e]), T(obj[b:e])))
+    return out
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port, kind 'port': the
-    reference is Python/PyTorch and cannot be installed as a package -- no setup.py; the
-    port was validated bit-for-bit against it, tests/golden) with all host threads."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.
+    kind "reference": the unmodified ADDLoss.eval_metrics (PyTorch eager, all intra-op threads) called the
+    way compare_all_models.py calls it; kind "port" (only when no reference checkout is reachable): the C
+    restatement oracle/pose_oracle.c on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pkg_w = importlib.import_module("6d-pose-estimation_b200.workloads")
+    import torch
+    W = importlib.import_module("6d-pose-estimation_b200.workloads")
     import oracle as O
     O.build()
     threads = O.max_threads()
-    pts, dia = pkg_w.config2_meshes(N_POINTS)
-    table = O.MeshTable(pts, dia)
-    # one step = a bounded sample of the workload: ~2-4 s of CPU work
-    probe, _, _ = cpu_rate(pkg_w, max(64, 8 * threads), threads)
-    sample = int(max(64, min(args.poses, probe * 3.0)))
-    pq, pt, gq, gt, obj = pkg_w.config2(sample)
-    for _ in range(args.warmup):
-        O.add_eval(table, pq[:sample // 4], pt[:sample // 4], gq[:sample // 4], gt[:sample // 4],
-                   obj[:sample // 4], n_threads=threads)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        O.add_eval(table, pq, pt, gq, gt, obj, n_threads=threads)
-    dt = time.perf_counter() - t0
+    root, crit = real_reference()
+    n_probe = max(256, 32 * threads)
+    port_probe, _, port_dt = cpu_rate(W, n_probe, threads)
+    port = {"value": port_probe, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_probe} poses, {port_dt:.2f} s, oracle/pose_oracle.c on all host threads"}
+    if root is None:
+        pts, dia = W.config2_meshes(N_POINTS)
+        table = O.MeshTable(pts, dia)
+        sample = int(max(64, min(args.poses, port_probe * 3.0)))
+        pq, pt, gq, gt, obj = W.config2(sample)
+        for _ in range(args.warmup):
+            O.add_eval(table, pq[:sample // 4], pt[:sample // 4], gq[:sample // 4], gt[:sample // 4],
+                       obj[:sample // 4], n_threads=threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.add_eval(table, pq, pt, gq, gt, obj, n_threads=threads)
+        dt = time.perf_counter() - t0
+        kind, cores = "port", threads
+        desc = (f"{sample} poses of config 2 per step x {args.steps} steps; oracle/pose_oracle.c on all host threads "
+                f"(bit-exact restatement); real reference unavailable: {crit}")
+    else:
+        poses = W.config2(4096)
+        t0 = time.perf_counter()
+        reference_eval_batches(crit, poses, 0, REF_BATCH)              # probe (also first-call warm-up)
+        probe = REF_BATCH / (time.perf_counter() - t0)
+        sample = int(min(1024, max(2 * REF_BATCH, round(probe * 2.5 / REF_BATCH) * REF_BATCH)))   # ~2.5 s per step
+        for k in range(args.warmup):
+            reference_eval_batches(crit, poses, 0, max(REF_BATCH, sample // 4))
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            lo = (k * sample) % (4096 - sample + 1)
+            reference_eval_batches(crit, poses, lo, lo + sample)
+        dt = time.perf_counter() - t0
+        kind, cores = "reference", torch.get_num_threads()
+        desc = (f"{sample} poses of config 2 per step x {args.steps} steps through the unmodified reference at "
+                f"{os.path.relpath(root, REPO) if root.startswith(REPO) else root} (models/add_loss.py ADDLoss.eval_metrics, "
+                f"batches of {REF_BATCH}, torch {torch.__version__} CPU eager, {cores} intra-op threads of "
+                f"{os.cpu_count()} host CPUs)")
     value = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": config_dict(args, {"sample_poses_per_step": sample}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"{sample} poses of config 2 per step x {args.steps} steps; oracle/pose_oracle.c on all "
-                                       "host threads (bit-exact restatement; the reference's own PyTorch-eager loop measured "
-                                       "46.5 poses/s on 8 cores for this mesh size, BASELINE.md section 2)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc, "port": port},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-def secondary_rooflines(pkg, dev, hbm_peak):
-    """Kernels (a), (c), (d1), (d2) at scaled batches, timed with CUDA events around the bare C-ABI
+def cpu_baseline_record(args, W, gpu_rows):
+    """The `cpu_baseline` object of our arm: the real reference (when reachable) timed on a bounded sample of
+    the same workload and its per-pose values compared with the GPU's; the oracle port beside it."""
+    import torch
+    from oracle import torch_eager as E
+    n_cpu = args.cpu_sample
+    if n_cpu <= 0:
+        probe, _, _ = cpu_rate(W, 256)
+        n_cpu = int(min(args.poses, max(256, probe * 10.0)))
+    v, cores, dt = cpu_rate(W, n_cpu)
+    port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {n_cpu} poses of the same config-2 workload, {dt:.1f} s, "
+                      "oracle/pose_oracle.c (C restatement, bit-exact vs the reference)"}
+    root, crit = real_reference()
+    if root is None:
+        port["reference_unavailable"] = crit
+        return port
+    poses = W.config2(4096)
+    n_ref = min(192, args.poses)
+    reference_eval_batches(crit, poses, 4096 - REF_BATCH, 4096)               # warm-up
+    t0 = time.perf_counter()
+    batches = reference_eval_batches(crit, poses, 0, n_ref)
+    dt = time.perf_counter() - t0
+    # per-pose values out of the reference (batch size 1: the aggregate of one pose is the pose) for the decision check
+    n_chk = min(64, n_ref)
+    r_add, r_adds, r_hit, r_valid = E.reference_eval_poses(crit, *(x[:n_chk] for x in poses))
+    u32 = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+    g = gpu_rows
+    hits_equal = bool(np.array_equal(r_hit, g["hit"][:n_chk]) and np.array_equal(r_valid, g["valid"][:n_chk]))
+    rec = {"value": n_ref / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+           "sample": f"first {n_ref} poses of the same config-2 workload in batches of {REF_BATCH}, {dt:.1f} s, through the "
+                     f"unmodified reference at {os.path.relpath(root, REPO) if root.startswith(REPO) else root} "
+                     f"(ADDLoss.eval_metrics, torch {torch.__version__} CPU eager, {torch.get_num_threads()} intra-op "
+                     f"threads of {os.cpu_count()} host CPUs)",
+           "reference_add_01d_acc_first_batch": float(batches[0]["add_01d_acc"]),
+           "decision_check": {"poses": n_chk, "hits_equal_gpu": hits_equal,
+                              "add_bits_equal": int((u32(r_add) == u32(g["add"][:n_chk])).sum()),
+                              "adds_bits_equal": int((u32(r_adds) == u32(g["adds"][:n_chk])).sum()),
+                              "how": "reference eval_metrics at batch size 1 on THIS box vs p6d_add_eval_host outputs"},
+           "port": port}
+    if not hits_equal:
+        raise AssertionError("ADD-0.1d decisions of the reference on this box differ from the GPU's: " + json.dumps(rec))
+    return rec
+
+
+# ------------------------------------------------------------------------- secondary kernels
+def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
+    """The other kernels of the path at scaled batches, timed with CUDA events around the bare C-ABI
     call (no Python wrapper in the timed region).  Algorithmic bytes per row: DESIGN.md section 4."""
     import torch
     core, W = pkg.core, pkg.workloads
@@ -214,7 +329,15 @@ def secondary_rooflines(pkg, dev, hbm_peak):
             best = min(best, a.elapsed_time(b) * 1e-3)
         return best
 
-    out = []
+    res = []
+
+    def hbm_row(kernel, rows, bpr, t, **extra):
+        r = {"kernel": kernel, "bound": "hbm", "rows": rows, "bytes_per_row": bpr, "us": round(t * 1e6, 1),
+             "achieved": rows * bpr / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+             "frac": rows * bpr / t / 1e9 / hbm_peak if hbm_peak else None}
+        r.update(extra)
+        res.append(r)
+
     n = 1 << 22
     g = torch.Generator(device=dev); g.manual_seed(7)
     rnd = lambda *shape: torch.randn(*shape, generator=g, device=dev)
@@ -224,31 +347,144 @@ def secondary_rooflines(pkg, dev, hbm_peak):
     t = timed(lambda: core.check(L.p6d_pose_loss_fwd_bwd(pq.data_ptr(), pt.data_ptr(), gq.data_ptr(), gt.data_ptr(), n, 1.0,
                                                          10.0, 0, o3.data_ptr(), g1.data_ptr(), g2.data_ptr(),
                                                          ws.data_ptr(), dev.index, st)))
-    out.append(("pose_loss_fwd_bwd (c)", n, 84, t))
+    hbm_row("pose_loss_fwd_bwd (c), geodesic", n, 84, t)
     z, uv = torch.rand(n, device=dev) + 0.4, torch.rand(n, 2, device=dev) * 400
-    K = torch.tensor(pkg.DEFAULT_K, dtype=torch.float32, device=dev).expand(n, 3, 3).contiguous()
+    K1 = torch.tensor(pkg.DEFAULT_K, dtype=torch.float32, device=dev).contiguous()
+    K = K1.expand(n, 3, 3).contiguous()
     o = torch.empty(n, 3, device=dev)
     t = timed(lambda: core.check(L.p6d_pinhole_fwd(z.data_ptr(), uv.data_ptr(), K.data_ptr(), 1, n, o.data_ptr(), dev.index, st)))
-    out.append(("pinhole_fwd (d1)", n, 60, t))
+    hbm_row("pinhole_fwd (d1), K [B,3,3]", n, 60, t)
+    t = timed(lambda: core.check(L.p6d_pinhole_fwd(z.data_ptr(), uv.data_ptr(), K1.data_ptr(), 0, n, o.data_ptr(), dev.index, st)))
+    hbm_row("pinhole_fwd (d1), shared K [3,3]", n, 24, t)
     m = 1 << 20
     d8 = torch.rand(m, 8, 8, device=dev) * 1.5
     uv8 = torch.rand(m, 2, device=dev) * 8
     o8 = torch.empty(m, 3, device=dev)
     t = timed(lambda: core.check(L.p6d_depth_backproject(d8.data_ptr(), 8, 8, uv8.data_ptr(), K.data_ptr(), 1, m, 7.0,
                                                          o8.data_ptr(), dev.index, st)))
-    out.append(("depth_backproject (d2), 8x8 crops (one 32-B sector of each 256-B crop is read)", m, 32 + 8 + 36 + 12, t))
-    res = [{"kernel": k, "bound": "hbm", "rows": rows, "bytes_per_row": bpr, "us": round(t * 1e6, 1),
-            "achieved": rows * bpr / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": rows * bpr / t / 1e9 / hbm_peak if hbm_peak else None} for k, rows, bpr, t in out]
-    # (a) ADD only is FP32-issue-bound, not HBM-bound: report poses/s
+    hbm_row("depth_backproject (d2), 8x8 crops, K [B,3,3] (one 32-B sector of each 256-B crop is read)", m, 32 + 8 + 36 + 12, t)
+    t = timed(lambda: core.check(L.p6d_depth_backproject(d8.data_ptr(), 8, 8, uv8.data_ptr(), K1.data_ptr(), 0, m, 7.0,
+                                                         o8.data_ptr(), dev.index, st)))
+    hbm_row("depth_backproject (d2), 8x8 crops, shared K [3,3]", m, 32 + 8 + 12, t)
+    # N1 / config 4 (ii): one 480x640 uint16 frame, 256 boxes (latency), and 2^20 boxes of the same frame (rate)
+    depth, boxes = W.config4_frame(40, 256)
+    dfr = torch.from_numpy(depth.view(np.int16)).to(dev).contiguous()        # uint16 bits
+    bx = torch.from_numpy(boxes).to(dev)
+    xyz = torch.empty(256, 3, device=dev)
+    t = timed(lambda: core.check(L.p6d_depth_crop_backproject(dfr.data_ptr(), 480, 640, bx.data_ptr(), 256, K1.data_ptr(), 224,
+                                                              xyz.data_ptr(), None, None, None, dev.index, st)), 20)
+    res.append({"kernel": "depth_crop_backproject (N1, config 4 ii): 480x640 uint16 frame, 256 boxes", "bound": "latency",
+                "boxes": 256, "us": round(t * 1e6, 2), "boxes_per_s": 256 / t})
+    big = bx.repeat(4096, 1).contiguous()
+    xyzb = torch.empty(big.shape[0], 3, device=dev)
+    t = timed(lambda: core.check(L.p6d_depth_crop_backproject(dfr.data_ptr(), 480, 640, big.data_ptr(), big.shape[0], K1.data_ptr(),
+                                                              224, xyzb.data_ptr(), None, None, None, dev.index, st)))
+    hbm_row("depth_crop_backproject (N1), 2^20 boxes of one frame (frame stays in L2: 16 B box + 12 B out per row)",
+            big.shape[0], 28, t)
+
+    # FP32-issue-bound rows: (a) ADD only, (b) ADD-S at the reference's mesh sizes
+    def fp32_row(kernel, poses, flop_per_pose, t, **extra):
+        r = {"kernel": kernel, "bound": "fp32-issue", "poses": poses, "us": round(t * 1e6, 1), "poses_per_s": poses / t,
+             "achieved": poses * flop_per_pose / t / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+             "frac": poses * flop_per_pose / t / 1e12 / fp32_peak if fp32_peak else None,
+             "flop_per_pose": flop_per_pose}
+        r.update(extra)
+        res.append(r)
+
     pts = {0: W.sphere_mesh(1000, 0.102, 100)}
     table = core.MeshTable(pts, {0: 0.102}, pkg.SYMMETRIC_OBJECT_IDS, dev)
     obj = torch.zeros(m, dtype=torch.int64, device=dev)
     qa, ta = torch.nn.functional.normalize(rnd(m, 4), dim=1), rnd(m, 3)
-    t = timed(lambda: table.evaluate(qa, ta, qa, ta, obj, want_adds=False), 5)
-    res.append({"kernel": "add_warp_kernel (a), N=1000", "bound": "fp32-issue", "poses": m, "us": round(t * 1e6, 1),
-                "poses_per_s": m / t, "hbm_gbs": m * 73 / t / 1e9})
+    qb, tb = torch.nn.functional.normalize(qa + 0.05 * rnd(m, 4), dim=1), ta + 0.005 * rnd(m, 3)
+    t = timed(lambda: table.evaluate(qb, tb, qa, ta, obj, want_adds=False), 5)
+    fp32_row("add_pose_kernel (a), ADD only, N=1000", m, 46 * 1000, t, hbm_gbs=m * 73 / t / 1e9)
+    for npts, Bn in ((500, 1 << 20), (1000, 1 << 18)):
+        pts = {9: W.box_mesh(npts, (0.1, 0.12, 0.05), 200 + npts)}
+        tb_ = core.MeshTable(pts, {9: 0.1646}, pkg.SYMMETRIC_OBJECT_IDS, dev)
+        ob = torch.full((Bn,), 9, dtype=torch.int64, device=dev)
+        t = timed(lambda: tb_.evaluate(qb[:Bn], tb[:Bn], qa[:Bn], ta[:Bn], ob, want_adds=True), 5)
+        fp32_row(f"adds_cta_kernel (b), ADD + ADD-S, N={npts}", Bn, 8 * npts * npts, t, schedule=tb_.schedule_state())
+    # the B = 32 training step through the public PoseLoss module (config 3): host latency, not a roofline
+    c = W.config3(32, 6)
+    Tn = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    crit = pkg.PoseLoss(1.0, 10.0, "geodesic")
+    rot, tr = Tn(c["rot_raw"]).requires_grad_(True), Tn(c["gt_trans"] + 0.01).requires_grad_(True)
+    gr, gtr = Tn(c["gt_rot"]), Tn(c["gt_trans"])
+
+    def train_step():
+        rot.grad = None; tr.grad = None
+        crit(rot, tr, gr, gtr).backward()
+    for _ in range(20):
+        train_step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        train_step()
+    torch.cuda.synchronize()
+    res.append({"kernel": "PoseLoss forward+backward through autograd, B=32 (config 3)", "bound": "latency",
+                "us_per_step": (time.perf_counter() - t0) / 200 * 1e6})
     return res
+
+
+# ------------------------------------------------------------------------- config 5
+def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barrier):
+    """BASELINE config 5 for one mesh size: 13 objects x 4 variants x n_per_block hypotheses, the hypothesis
+    axis of every block sliced over the ranks (strong scaling), one native call per rank
+    (p6d_sweep_run) + one all-reduce of the accumulators.  The first poses of every block of every rank's
+    slice are re-evaluated by the oracle after the timed region."""
+    import torch
+    import torch.distributed as dist
+    import oracle as O
+    W = pkg.workloads
+    variants = pkg.sweep.VARIANTS
+    pts, dia = W.sweep_meshes(n_points)
+    ev = pkg.PoseEvaluator(pts, dia, dev, n_rows=len(variants))
+    # warm-up through the same code path (also runs the one-time self-check of a re-laid kernel)
+    pkg.evaluate_sweep(pts, dia, dev, 4096 * world, seed=SWEEP_SEED, rank=rank, world=world, evaluator=ev)
+    ev.acc.zero_()
+    cn = max(8, check_total // world)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    acc, launches, check = pkg.evaluate_sweep(pts, dia, dev, n_per_block, seed=SWEEP_SEED, rank=rank, world=world,
+                                              evaluator=ev, check_n=cn)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    tm = torch.tensor([wall, e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    wall_s, dev_s = (float(x) for x in tm.tolist())
+    # oracle check of what was evaluated (outside the timed region)
+    nb, k = check["pq"].shape[0], check["pq"].shape[1]
+    rows = lambda name, w: np.ascontiguousarray(check[name].reshape(nb * k, w))
+    ref = O.add_eval(O.MeshTable(pts, dia), rows("pq", 4), rows("pt", 3), rows("gq", 4), rows("gt", 3),
+                     np.ascontiguousarray(check["obj"].reshape(-1)), n_threads=max(1, O.max_threads() // world))
+    u32 = lambda a: np.ascontiguousarray(a, np.float32).reshape(-1).view(np.uint32)
+    bad = int((u32(check["add"]) != u32(ref[0])).sum() + (u32(check["adds"]) != u32(ref[1])).sum()
+              + (check["hit"].reshape(-1) != ref[2]).sum())
+    chk = torch.tensor([bad, nb * k], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(chk)
+    hits, valid = acc.hits.cpu().numpy(), acc.valid.cpu().numpy()
+    total = int(valid.sum())
+    ids = sorted(pts)
+    table = [[int(hits[v, o]) for o in ids] for v in range(len(variants))]
+    return {"workload": f"BASELINE config 5: {len(ids)} objects x {len(variants)} variants x {n_per_block} hypotheses, "
+                        f"{n_points}-point meshes, ADD + ADD-S + ADD-0.1d for every pose; hypotheses generated on the device "
+                        "(p6d_synth_poses), translations of the geometric variants by kernels (d1) / (d2)",
+            "n_points": n_points, "hypotheses": total, "scaling": "strong", "n_gpus": world,
+            "seconds": wall_s, "device_seconds": dev_s, "poses_per_s": total / wall_s,
+            "tflops": total * (8 * n_points * n_points + 46 * n_points) / wall_s / 1e12,
+            "launches_per_rank": launches,
+            "hits_per_variant": {v: int(hits[i].sum()) for i, v in enumerate(variants)},
+            "valid_per_variant": {v: int(valid[i].sum()) for i, v in enumerate(variants)},
+            "hits_table_objects": ids, "hits_table": table,
+            "hits_table_sha256": hashlib.sha256(json.dumps(table).encode()).hexdigest()[:16],
+            "oracle_check": {"poses": int(chk[1]), "mismatches": int(chk[0]),
+                             "what": f"first {k} hypotheses of every (object, variant) block of every rank's slice: ADD, ADD-S "
+                                     "bits and decisions vs oracle/pose_oracle.c"}}
 
 
 # ------------------------------------------------------------------------- GPU arm
@@ -265,8 +501,6 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keeps stdout to the one JSON line of the contract
         dist.init_process_group("nccl", device_id=dev)
 
     pkg = importlib.import_module("6d-pose-estimation_b200")
@@ -330,26 +564,37 @@ def run_b200(args):
     total_ms = float(dev_ms.item())
     value = world * B * args.steps / (total_ms * 1e-3)
     timed_launches = launches
+    sched = table.schedule_state()
 
     # result sanity on the numbers just computed (accuracy is counts / totals, integer-exact)
     hits = int(acc[0].sum().item()); valid = int(acc[1].sum().item())
     assert valid == B, (valid, B)
 
     # ---------------- end-to-end: host buffers in, host results out, through the C ABI
-    h_np = [t.numpy() for t in pinned]
-    for _ in range(2):
-        table.evaluate_host(*h_np, want_adds=True, per_pose=True)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        r = table.evaluate_host(*h_np, want_adds=True, per_pose=True)
-    torch.cuda.synchronize()
-    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * e2e_steps / float(e2e_dt.item())
+    def e2e(bufs):
+        for _ in range(2):
+            table.evaluate_host(*bufs, want_adds=True, per_pose=True)
+        barrier()
+        t0 = time.perf_counter()
+        steps = max(3, min(args.steps, 10))
+        for _ in range(steps):
+            r = table.evaluate_host(*bufs, want_adds=True, per_pose=True)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return world * B * steps / float(dt.item()), steps, r
+
+    e2e_value, e2e_steps, r = e2e([t.numpy() for t in pinned])
     assert int(r["obj_hits"].sum()) == hits, "host-entry decisions differ from the device entry"
+    e2e_pageable, _, r2 = e2e([np.array(x, copy=True) for x in host])        # a caller's ordinary NumPy arrays
+    assert int(r2["obj_hits"].sum()) == hits
+
+    # ---------------- BASELINE config 5, strong scaling (every rank takes part)
+    sweeps = {}
+    if not args.no_sweep and B == POSES_PER_GPU:
+        for npts in [int(x) for x in args.sweep_points.split(",") if x]:
+            sweeps[f"n{npts}"] = sweep_record(pkg, dev, rank, world, npts, args.sweep_per_block, args.sweep_check, barrier)
 
     if rank == 0:
         kernel_ms = float(np.mean(step_ms))            # rank 0's kernel; at N = 1 the step is the kernel
@@ -362,50 +607,50 @@ def run_b200(args):
         sm_max = float(peaks.get("sm_max_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
         nominal = info["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
         tr = profiled_traffic() if B == POSES_PER_GPU else None
-        relaid = bool(core.lib().p6d_adds_schedule())
-        roof = {"bound": "fp32", "achieved": achieved, "peak": nominal, "unit": "TFLOP/s",
+        relaid = sched["built_relaid"] == 1 and sched["runtime_state"] == 1
+        mb = {}
+        if not args.no_microbench:
+            for kind, name in ((0, "ffma"), (1, "ffma2"), (2, "adds_mix")):
+                mb[name] = round(max(core.fp32_microbench(kind, local, 4000)[0] for _ in range(3)), 2)
+        peak = mb.get("ffma2") or nominal
+        roof = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "kernel": ("adds_cta_kernel<256,8,2,deferred minima>, scan loop re-laid after linking by "
-                           "csrc/sass_sched.py") if relaid else "adds_cta_kernel<512,4,2,2> (ptxas schedule)",
-                "frac": achieved / nominal, "traffic": tr["bytes"] if tr else None,
+                           "csrc/sass_sched.py, verified against the ptxas-scheduled kernel on this device before use")
+                if relaid else "adds_cta_kernel<512,4,2,2> (ptxas schedule)",
+                "schedule_state": sched,
+                "frac": achieved / peak, "traffic": tr["bytes"] if tr else None,
                 "traffic_source": tr["source"] if tr else None,
                 "algorithmic_bytes_per_launch": B * BYTES_PER_POSE,
-                "peak_source": f"nominal FFMA peak {info['sm_count']} SM x 128 lanes x 2 FLOP x {sm_max:.0f} MHz "
-                               "(sm_max_mhz of MEASURED_PEAKS.json; that file has no FP32 entry -- the kernel "
-                               "is neither HBM- nor tensor-bound, SURVEY 7.3.2)",
+                "peak_source": ("FFMA2 issue-rate microbenchmark measured in this run (p6d_fp32_microbench kind 1); "
+                                "MEASURED_PEAKS.json has no FP32 entry -- the kernel is neither HBM- nor tensor-bound "
+                                "(SURVEY 7.3.2)") if mb.get("ffma2") else "nominal (microbenchmark skipped)",
+                "peak_nominal": nominal, "frac_of_nominal": achieved / nominal,
+                "peak_nominal_source": f"{info['sm_count']} SM x 128 lanes x 2 FLOP x {sm_max:.0f} MHz",
                 "algorithmic_flop_per_pose": FLOP_PER_POSE,
                 "hbm": {"achieved_gbs": B * BYTES_PER_POSE / (kernel_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "note": "of measured; informational"}}
-        if not args.no_microbench:
-            mb = {}
-            for kind, name in ((0, "ffma"), (1, "ffma2"), (2, "adds_mix")):
-                mb[name] = round(max(core.fp32_microbench(kind, local, 4000)[0] for _ in range(3)), 2)
+        if mb:
             roof["measured_fp32_tflops"] = mb
-            roof["frac_of_measured_mix"] = achieved / mb["adds_mix"] if mb["adds_mix"] else None
-            roof["measured_mix_note"] = ("adds_mix = the scan tile on register operands as ptxas schedules it; the "
-                                         "product loop is re-laid after linking, so a ratio above 1 is expected")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args), "roofline": roof, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes"],
                         "d2h_bytes_per_step": r["d2h_bytes"], "steps": e2e_steps,
-                        "api": "p6d_add_eval_host via MeshTable.evaluate_host (pinned host buffers)"},
+                        "api": "p6d_add_eval_host via MeshTable.evaluate_host (pinned host buffers)",
+                        "pageable_value": e2e_pageable,
+                        "pageable_note": "same call with ordinary (pageable) NumPy arrays as a caller would pass them"},
                 "gpu_launches": timed_launches, "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
                 "add_01d_acc": 100.0 * hits / valid}
+        if sweeps:
+            line["sweep"] = sweeps
         if not args.no_secondary and B == POSES_PER_GPU:
             try:
-                line["secondary_rooflines"] = secondary_rooflines(pkg, dev, peaks.get("hbm_gbs"))
+                line["secondary"] = secondary_rooflines(pkg, dev, peaks.get("hbm_gbs"), peak)
             except Exception as e:  # never lose the headline line over the side measurements
-                line["secondary_rooflines"] = {"error": repr(e)}
+                line["secondary"] = {"error": repr(e)}
         if not args.no_cpu_baseline:
-            n_cpu = args.cpu_sample
-            if n_cpu <= 0:
-                probe, _, _ = cpu_rate(W, 256)
-                n_cpu = int(min(B, max(256, probe * 12.0)))
-            v, cores, dt = cpu_rate(W, n_cpu)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"first {n_cpu} poses of the same config-2 workload, {dt:.1f} s, "
-                                              "oracle/pose_oracle.c (C restatement, bit-exact vs the reference)"}
+            line["cpu_baseline"] = cpu_baseline_record(args, W, r)
         emit(line)
     if world > 1:
         dist.barrier()
