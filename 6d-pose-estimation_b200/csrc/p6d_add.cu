@@ -495,7 +495,7 @@ static bool class_is_relaid(int cls) { return p6d_sched_state[16 + cls] == 't'; 
 // agree; on any difference the class falls back to the ptxas kernel for the rest of the process.
 //   0 = not checked yet, 1 = verified, 2 = rejected
 static std::atomic<int> g_relaid_state[64][3];
-static std::mutex g_config_mu;                 // launch configuration + self-check (cold paths only)
+static std::recursive_mutex g_config_mu;                // launch configuration + self-check (cold paths only)
 static size_t g_smem_raised[64][P6D_MAX_VARIANTS];   // per-device opt-in shared memory, only ever raised
 
 static bool relaid_disabled_by_env() {
@@ -524,7 +524,7 @@ static int pick_variant(const p6d_mesh_table* t, bool loss, cudaStream_t st, int
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (st && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
             return P6D_OK;       // cannot synchronise inside a capture: this launch keeps ptxas' schedule
-        std::lock_guard<std::mutex> lock(g_config_mu);
+        std::lock_guard<std::recursive_mutex> lock(g_config_mu);
         sv = state.load(std::memory_order_acquire);
         if (sv == 0) {
             int64_t bad = 0;
@@ -575,7 +575,7 @@ static int adds_max_points_for(int smem_limit) {
 static int configure_variant(const p6d_mesh_table* t, int vi, size_t smem, int* per_sm) {
     int v = __atomic_load_n(&t->adds_per_sm[vi], __ATOMIC_ACQUIRE);
     if (v > 0) { *per_sm = v; return P6D_OK; }
-    std::lock_guard<std::mutex> lock(g_config_mu);
+    std::lock_guard<std::recursive_mutex> lock(g_config_mu);
     int limit = 0;
     int rc = max_optin_smem(t->device, &limit);
     if (rc) return rc;
@@ -770,7 +770,7 @@ int p6d_adds_selfcheck(const p6d_mesh_table* table, int64_t n_poses, int64_t* mi
     if (!class_is_relaid(cls)) return P6D_OK;      // nothing re-laid in this build: nothing to compare
     DeviceGuard guard(table->device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
-    std::lock_guard<std::mutex> lock(g_config_mu);
+    std::lock_guard<std::recursive_mutex> lock(g_config_mu);
     const int rc = selfcheck_class(table, cls, n_poses, mismatches);
     if (rc) return rc;
     std::atomic<int>& state = g_relaid_state[table->device & 63][cls];

@@ -12,7 +12,12 @@
 //                  in ATen's summation order, so the L1 rotation term and the translation
 //                  term equal the CPU reference bit for bit (atan2f differs by <= 2 ulp);
 //   B >  SMALL_B : grid-stride rows, float64 block partials + atomics, last block
-//                  finalises (HBM-bound shape used for the GB/s measurement).
+//                  finalises (HBM-bound shape used for the GB/s measurement).  The sum order is
+//                  not ATen's there, so nothing is bit-exact by construction (bar: 1e-5); the
+//                  geodesic mode therefore runs the FAST row: reciprocal square roots and
+//                  multiplications (MUFU.RSQ / MUFU.RCP, <= 2 ulp each) instead of 4 IEEE square
+//                  roots and 13 IEEE divisions per row, which halves the instruction count and
+//                  lets the loads of the next rows overlap the arithmetic.
 #include "p6d_common.cuh"
 
 namespace p6d {
@@ -41,7 +46,13 @@ __device__ __forceinline__ float norm4(const float* v) {
     return __fsqrt_rn(s);
 }
 
-// pt_row / gt_row / grad_t_row point at the 3 floats of row b
+__device__ __forceinline__ float sumsq4(const float* v) {
+    return fmaf(v[3], v[3], fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0])));
+}
+
+// pt_row / gt_row / grad_t_row point at the 3 floats of row b.
+// FAST (large batches, geodesic mode only): see the header comment.
+template <bool FAST>
 __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* pt_row,
                                            const float* __restrict__ gq, const float* gt_row,
                                            int64_t b, int64_t B, float wr, float wt, int mode,
@@ -51,14 +62,31 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
     const float4 c4 = *reinterpret_cast<const float4*>(gq + 4 * b);
     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
     const float c[4] = {c4.x, c4.y, c4.z, c4.w};
-    const float na_raw = norm4(a), nc_raw = norm4(c);
-    const float na = na_raw > 1e-12f ? na_raw : 1e-12f;
-    const float nc = nc_raw > 1e-12f ? nc_raw : 1e-12f;
     float u[4], v[4];
+    float na = 1.0f, inv_na = 1.0f;      // max(|a|, 1e-12) (exact row) or its reciprocal (FAST row)
+    bool a_has_norm_grad;
+    if (FAST) {
+        const float sa = sumsq4(a), sc = sumsq4(c);
+        // |x| >= 1e-12  <=>  |x|^2 >= 1e-24 (a normal float32)
+        inv_na = sa >= 1e-24f ? rsqrtf(sa) : 1e12f;
+        const float inv_nc = sc >= 1e-24f ? rsqrtf(sc) : 1e12f;
+        a_has_norm_grad = sa >= 1e-24f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        u[k] = __fdiv_rn(a[k], na);
-        v[k] = __fdiv_rn(c[k], nc);
+        for (int k = 0; k < 4; ++k) {
+            u[k] = a[k] * inv_na;
+            v[k] = c[k] * inv_nc;
+        }
+    } else {
+        const float na_raw = norm4(a), nc_raw = norm4(c);
+        na = na_raw > 1e-12f ? na_raw : 1e-12f;
+        const float nc = nc_raw > 1e-12f ? nc_raw : 1e-12f;
+        // clamp_min passes the gradient of the norm only when |a| >= eps; norm'(0) = 0
+        a_has_norm_grad = na_raw >= 1e-12f && na_raw > 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u[k] = __fdiv_rn(a[k], na);
+            v[k] = __fdiv_rn(c[k], nc);
+        }
     }
     // Gradient math runs in float32: the two terms of gu are orthogonal (u-v is
     // perpendicular to u+v) and gu is already tangent to the unit sphere, so nothing cancels;
@@ -79,13 +107,26 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
             d[k] = __fsub_rn(u[k], v[k]);
             s[k] = __fadd_rn(u[k], v[k]);
         }
-        const float dn = norm4(d), sn = norm4(s);
+        float dn, sn, cd, cs;
+        if (FAST) {
+            const float sd = sumsq4(d), ss = sumsq4(s);
+            const float rd = sd > 0.0f ? rsqrtf(sd) : 0.0f, rs = ss > 0.0f ? rsqrtf(ss) : 0.0f;
+            dn = sd * rd;
+            sn = ss * rs;
+            const float den = sd + ss;
+            const float inv_den = den > 0.0f ? __fdividef(2.0f, den) : 0.0f;
+            cd = sn * inv_den * rd;
+            cs = -(dn * inv_den * rs);
+        } else {
+            dn = norm4(d);
+            sn = norm4(s);
+            const float den = fmaf(dn, dn, sn * sn);
+            const float inv_den = den > 0.0f ? __fdiv_rn(2.0f, den) : 0.0f;
+            // d(angle)/d(dn) * 1/dn  and  d(angle)/d(sn) * 1/sn  (norm'(0) = 0)
+            cd = dn > 0.0f ? __fdiv_rn(sn * inv_den, dn) : 0.0f;
+            cs = sn > 0.0f ? -__fdiv_rn(dn * inv_den, sn) : 0.0f;
+        }
         o.rot = __fmul_rn(2.0f, atan2f(dn, sn));
-        const float den = fmaf(dn, dn, sn * sn);
-        const float inv_den = den > 0.0f ? __fdiv_rn(2.0f, den) : 0.0f;
-        // d(angle)/d(dn) * 1/dn  and  d(angle)/d(sn) * 1/sn  (norm'(0) = 0)
-        const float cd = dn > 0.0f ? __fdiv_rn(sn * inv_den, dn) : 0.0f;
-        const float cs = sn > 0.0f ? -__fdiv_rn(dn * inv_den, sn) : 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) gu[k] = fmaf(cd, d[k], cs * s[k]);
     } else {
@@ -115,9 +156,8 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
         float gdotu = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) gdotu = fmaf(gu[k], u[k], gdotu);
-        // clamp_min passes the gradient of the norm only when |a| >= eps; norm'(0) = 0
-        const float proj = (na_raw >= 1e-12f && na_raw > 0.0f) ? gdotu : 0.0f;
-        const float scale = __fdiv_rn(__fdiv_rn(wr, (float)B), na);
+        const float proj = a_has_norm_grad ? gdotu : 0.0f;
+        const float scale = FAST ? __fdiv_rn(wr, (float)B) * inv_na : __fdiv_rn(__fdiv_rn(wr, (float)B), na);
         float4 g4;
         float* gp = reinterpret_cast<float*>(&g4);
 #pragma unroll
@@ -146,12 +186,13 @@ struct Geo {
     float* trans_out;    // [B,3] nullable: the translation the reference's model would return
 };
 
+template <bool FAST>
 __device__ __forceinline__ RowOut loss_row_any(const float* __restrict__ pq, const float* __restrict__ pt,
                                                const float* __restrict__ gq, const float* __restrict__ gt,
                                                int64_t b, int64_t B, float wr, float wt, int mode,
                                                float* __restrict__ grad_q, float* __restrict__ grad_t,
                                                const Geo& geo) {
-    if (!geo.z) return loss_row(pq, pt + 3 * b, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q,
+    if (!geo.z) return loss_row<FAST>(pq, pt + 3 * b, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q,
                                 grad_t ? grad_t + 3 * b : nullptr);
     const float* k = geo.K + (geo.k_batched ? 9 * b : 0);
     const float fx = __ldg(k + 0), cx = __ldg(k + 2), fy = __ldg(k + 4), cy = __ldg(k + 5);
@@ -160,7 +201,7 @@ __device__ __forceinline__ RowOut loss_row_any(const float* __restrict__ pq, con
     const float du = __fsub_rn(c.x, cx), dv = __fsub_rn(c.y, cy);
     float t3[3] = {__fdiv_rn(__fmul_rn(du, zz), fx), __fdiv_rn(__fmul_rn(dv, zz), fy), zz};
     float g3[3] = {0.0f, 0.0f, 0.0f};
-    const RowOut o = loss_row(pq, t3, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q, geo.grad_z ? g3 : nullptr);
+    const RowOut o = loss_row<FAST>(pq, t3, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q, geo.grad_z ? g3 : nullptr);
     if (geo.trans_out) {
         geo.trans_out[3 * b + 0] = t3[0];
         geo.trans_out[3 * b + 1] = t3[1];
@@ -188,7 +229,7 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq
     __shared__ float s_rot[SMALL_B];
     __shared__ float s_ad[3 * SMALL_B];
     for (int b = threadIdx.x; b < B; b += LOSS_T) {
-        const RowOut o = loss_row_any(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
+        const RowOut o = loss_row_any<false>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         s_rot[b] = o.rot;
         s_ad[3 * b] = o.ad[0];
         s_ad[3 * b + 1] = o.ad[1];
@@ -207,6 +248,7 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq
 // Measured alternatives at 4 M rows (all slower than this shape, 91-94 us): prefetch.global.L1 of the
 // thread's next row (101 us), two rows per thread and trip (120 us, 80 registers), 6 CTAs per SM at
 // 40 registers (102 us, spills), shared-memory tile staging of the [B,3] rows (100 us).
+template <bool FAST>
 __global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq, const float* pt, const float* gq,
                                                                  const float* gt, int64_t B, float wr, float wt,
                                                                  int mode, float* out, float* grad_q,
@@ -214,7 +256,7 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq
     double rs = 0.0, ts = 0.0;
     // (prefetching the next row of the thread with prefetch.global.L1 was tried: 10 % slower)
     for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * LOSS_T) {
-        const RowOut o = loss_row_any(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
+        const RowOut o = loss_row_any<FAST>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         rs += (double)o.rot;
         ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
     }
@@ -272,9 +314,16 @@ static int launch_pose_loss(const float* pq, const float* pt, const float* gq, c
         int64_t blocks = (B + LOSS_T - 1) / LOSS_T;
         const int64_t cap = (int64_t)sms * 8;
         if (blocks > cap) blocks = cap;
-        pose_loss_large_kernel<<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
-                                                                    mode, out, grad_q, grad_t,
-                                                                    static_cast<Workspace*>(workspace), geo);
+        // geodesic: FAST row (nothing is bit-exact at this size anyway); quaternion-L1: exact row, because
+        // its sub-gradient is a sign pattern that a 1-ulp change of u - v could flip
+        if (mode == 0)
+            pose_loss_large_kernel<true><<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
+                                                                              mode, out, grad_q, grad_t,
+                                                                              static_cast<Workspace*>(workspace), geo);
+        else
+            pose_loss_large_kernel<false><<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
+                                                                               mode, out, grad_q, grad_t,
+                                                                               static_cast<Workspace*>(workspace), geo);
     }
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;

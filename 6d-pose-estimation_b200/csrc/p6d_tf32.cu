@@ -75,9 +75,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// bounded wait: a malformed descriptor must end in an error, not in a hung GPU
+// bounded wait (0.25 s of %globaltimer): a malformed descriptor must end in an error, not in a hung GPU
 __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
         uint32_t ok;
         asm volatile(
             "{\n\t"
@@ -89,8 +90,13 @@ __device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (ok) return true;
+        if ((spin & 63u) == 63u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 250000000ull) return false;
+        }
     }
-    return false;
 }
 
 // 32 consecutive accumulator columns of this thread's row

@@ -263,7 +263,7 @@ def test_batch_beyond_the_launch_limit_is_refused(pkg, cuda_dev, W):
     out = torch.zeros(64, dtype=torch.uint8, device=cuda_dev)
     L, ptr = pkg.core.lib(), pkg.core.ptr
     rc = L.p6d_add_eval(table.handle, ptr(buf), ptr(buf), ptr(buf), ptr(buf), ptr(obj), None, 2 ** 31,
-                        ptr(buf), ptr(buf), ptr(out), ptr(out), None, None)
+                        ptr(buf), ptr(buf), ptr(out), ptr(out), None, None, None)
     assert rc == pkg.core.P6D_EINVAL and b"split the batch" in L.p6d_last_error()
     torch.cuda.synchronize(cuda_dev)
 
