@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(CAM_T) depth_backproject_kernel(const float* _
         long long vi = (v != v) ? LLONG_MIN : (long long)v;
         ui = ui < 0 ? 0 : (ui > hi ? hi : ui);
         vi = vi < 0 ? 0 : (vi > hi ? hi : vi);
-        float zz = __ldg(depth + ((int64_t)b * H + vi) * W + ui);
+        // one pixel per crop: ask L2 for the smallest fetch it offers (64 B; the default promotes a
+        // miss to 128 B, which was 2/3 of this kernel's DRAM traffic) and keep the line out of L1
+        float zz;
+        asm("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(zz) : "l"(depth + ((int64_t)b * H + vi) * W + ui));
         zz = (zz > 0.01f) ? zz : 0.5f;  // false for NaN -> 0.5
         zz = clamp_keep_nan(zz, 0.1f, 2.0f);
         out[3 * b + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(u, cx), zz), fx);
@@ -90,9 +93,23 @@ __global__ void __launch_bounds__(CAM_T) depth_backproject_kernel(const float* _
 // traffic per box -- and the network then reads ONE pixel of the result
 // (models/pose_net_rgbd_geometric.py:69-75).  Here one thread per box computes the crop
 // geometry (Python int / float64 semantics), the remapped centre and K_crop (NumPy
-// float32 semantics), evaluates cv2's generic bilinear formula at that single pixel from
-// 4 texels of the original frame (zero outside the frame = the constant border), and
-// back-projects.
+// float32 semantics), evaluates cv2's bilinear formula at that single pixel from 4 texels of the
+// original frame (zero outside the frame = the constant border), and back-projects.
+// cv2.resize on CV_16U has two arithmetics (oracle.resize_linear_u16, tests/test_live_pins.py):
+//   bilinear 0  the pip wheel's default, i.e. what the reference's call computes: IPP's
+//               ippiResizeLinear_16u -- float64 source coordinate, float32 weight, horizontal then
+//               vertical lerp as one fma(b - a, w, a) each, round half to even;
+//   bilinear 1  OpenCV's own C++ path (no IPP): float32 coordinate, a*(1-w) + b*w with separate
+//               roundings, and INTER_AREA ((a+b+c+d+2) >> 2) when the crop is exactly 2x the output.
+__device__ __forceinline__ void resize_axis_ipp(int d, long long cs, int img, int& s0, int& s1, float& w) {
+    const double c = __dsub_rn(__dmul_rn((double)d + 0.5, (double)cs / (double)img), 0.5);
+    const double fl = floor(c);
+    const long long s = (long long)fl;
+    w = s < 0 ? 0.0f : (float)__dsub_rn(c, fl);
+    s0 = (int)(s < 0 ? 0 : (s > cs - 1 ? cs - 1 : s));
+    s1 = (int)(s + 1 < 0 ? 0 : (s + 1 > cs - 1 ? cs - 1 : s + 1));
+}
+
 __device__ __forceinline__ void resize_axis(int d, long long cs, int img, int& s0, int& s1, float& w0, float& w1) {
     const double scale = 1.0 / ((double)img / (double)cs);
     const float v = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
@@ -108,7 +125,7 @@ __device__ __forceinline__ void resize_axis(int d, long long cs, int img, int& s
 
 __global__ void __launch_bounds__(CAM_T) depth_crop_backproject_kernel(
     const unsigned short* __restrict__ depth, int H, int W, const int* __restrict__ boxes, int64_t B,
-    const float* __restrict__ K, int img, float* __restrict__ xyz, float* __restrict__ center_out,
+    const float* __restrict__ K, int img, int bilinear, float* __restrict__ xyz, float* __restrict__ center_out,
     float* __restrict__ kcrop_out, unsigned short* __restrict__ zmm_out) {
     const float fx = __ldg(K + 0), cx = __ldg(K + 2), fy = __ldg(K + 4), cy = __ldg(K + 5);
     for (int64_t b = (int64_t)blockIdx.x * CAM_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * CAM_T) {
@@ -143,18 +160,33 @@ __global__ void __launch_bounds__(CAM_T) depth_crop_backproject_kernel(
         int ui = (int)u, vi = (int)v;              // .long(): truncation, then clamp
         ui = ui < 0 ? 0 : (ui > img - 1 ? img - 1 : ui);
         vi = vi < 0 ? 0 : (vi > img - 1 ? img - 1 : vi);
-        int sx0, sx1, sy0, sy1;
-        float a0, a1, b0, b1;
-        resize_axis(ui, cs, img, sx0, sx1, a0, a1);
-        resize_axis(vi, cs, img, sy0, sy1, b0, b1);
         auto texel = [&](int yy, int xx) -> float {
             const long long fy_ = y1 + yy - pad_t, fx_ = x1 + xx - pad_l;
             if (fy_ < 0 || fy_ >= H || fx_ < 0 || fx_ >= W) return 0.0f;   // cv2.copyMakeBorder(..., value=0)
             return (float)__ldg(depth + fy_ * W + fx_);
         };
-        const float h0 = __fadd_rn(__fmul_rn(texel(sy0, sx0), a0), __fmul_rn(texel(sy0, sx1), a1));
-        const float h1 = __fadd_rn(__fmul_rn(texel(sy1, sx0), a0), __fmul_rn(texel(sy1, sx1), a1));
-        const float val = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+        int sx0, sx1, sy0, sy1;
+        float val;
+        if (bilinear == 0) {                        // IPP (the reference's default cv2.resize)
+            float wx, wy;
+            resize_axis_ipp(ui, cs, img, sx0, sx1, wx);
+            resize_axis_ipp(vi, cs, img, sy0, sy1, wy);
+            const float t00 = texel(sy0, sx0), t01 = texel(sy0, sx1), t10 = texel(sy1, sx0), t11 = texel(sy1, sx1);
+            const float h0 = __fmaf_rn(__fsub_rn(t01, t00), wx, t00);
+            const float h1 = __fmaf_rn(__fsub_rn(t11, t10), wx, t10);
+            val = __fmaf_rn(__fsub_rn(h1, h0), wy, h0);
+        } else if (cs == 2ll * img) {               // OpenCV C++ path, exact 2x: INTER_AREA, rounds half up
+            const int q = (int)texel(2 * vi, 2 * ui) + (int)texel(2 * vi, 2 * ui + 1) + (int)texel(2 * vi + 1, 2 * ui) +
+                          (int)texel(2 * vi + 1, 2 * ui + 1);
+            val = (float)((q + 2) >> 2);
+        } else {                                    // OpenCV C++ path
+            float a0, a1, b0, b1;
+            resize_axis(ui, cs, img, sx0, sx1, a0, a1);
+            resize_axis(vi, cs, img, sy0, sy1, b0, b1);
+            const float h0 = __fadd_rn(__fmul_rn(texel(sy0, sx0), a0), __fmul_rn(texel(sy0, sx1), a1));
+            const float h1 = __fadd_rn(__fmul_rn(texel(sy1, sx0), a0), __fmul_rn(texel(sy1, sx1), a1));
+            val = __fadd_rn(__fmul_rn(h0, b0), __fmul_rn(h1, b1));
+        }
         int zi = __float2int_rn(val);              // saturate_cast<ushort>(cvRound)
         zi = zi < 0 ? 0 : (zi > 65535 ? 65535 : zi);
         float z = __fdiv_rn((float)zi, 1000.0f);
@@ -273,9 +305,10 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
 }
 
 int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes, int64_t B,
-                               const float* K, int img_size, float* xyz, float* center, float* kcrop,
+                               const float* K, int img_size, int bilinear, float* xyz, float* center, float* kcrop,
                                uint16_t* z_mm, int device, void* stream) {
-    if (B < 0 || H < 1 || W < 1 || img_size < 1 || (B > 0 && (!depth || !boxes || !K || !xyz))) {
+    if (B < 0 || H < 1 || W < 1 || img_size < 1 || (bilinear != 0 && bilinear != 1) ||
+        (B > 0 && (!depth || !boxes || !K || !xyz))) {
         set_error("p6d_depth_crop_backproject: bad arguments");
         return P6D_EINVAL;
     }
@@ -286,7 +319,7 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
     int rc = grid_for(B, device, &grid);
     if (rc) return rc;
     depth_crop_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
-        depth, H, W, boxes, B, K, img_size, xyz, center, kcrop, z_mm);
+        depth, H, W, boxes, B, K, img_size, bilinear, xyz, center, kcrop, z_mm);
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;
 }

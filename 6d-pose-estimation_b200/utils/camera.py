@@ -132,12 +132,17 @@ def depth_backproject(depth_raw, bbox_center, camera_matrix, clamp_hi=223.0):
 
 
 @torch.no_grad()
-def depth_crop_backproject(depth_frame, boxes, camera_matrix, img_size=224, return_aux=False):
+def depth_crop_backproject(depth_frame, boxes, camera_matrix, img_size=224, return_aux=False, bilinear="cv2"):
     """XYZ for every (x, y, w, h) box of one uint16 depth frame [H,W] (millimetres) without
     materialising any crop: the reference's pad / square-crop / cv2.resize / K remap
     (data/dataset_rgbd.py:104-179) fused with its depth back-projection
     (models/pose_net_rgbd_geometric.py:56-85).  `camera_matrix` is the frame's [3,3] K.
-    With return_aux also returns (centre [B,2], K_crop [B,3,3], z_mm [B] uint16)."""
+    With return_aux also returns (centre [B,2], K_crop [B,3,3], z_mm [B] uint16).
+    `bilinear`: "cv2" reproduces what ``cv2.resize`` of the OpenCV pip wheel computes for uint16 (its
+    IPP path -- the reference's own call), "generic" OpenCV's C++ path (a build without IPP or
+    ``cv2.ipp.setUseIPP(False)``); the two differ by 1 mm in 0.1-10 % of the pixels."""
+    if bilinear not in ("cv2", "generic"):
+        raise ValueError("bilinear must be 'cv2' or 'generic'")
     core = _core()
     if not isinstance(depth_frame, torch.Tensor):
         depth_frame = torch.from_numpy(np.ascontiguousarray(depth_frame, dtype=np.uint16))
@@ -159,7 +164,7 @@ def depth_crop_backproject(depth_frame, boxes, camera_matrix, img_size=224, retu
     kcrop = torch.empty(B, 3, 3, dtype=torch.float32, device=dev) if return_aux else None
     zmm = torch.empty(B, dtype=torch.int16, device=dev) if return_aux else None
     core.check(core.lib().p6d_depth_crop_backproject(core.ptr(d), H, W, core.ptr(bx), B, core.ptr(K), int(img_size),
-                                                     core.ptr(xyz), core.ptr(center), core.ptr(kcrop), core.ptr(zmm),
+                                                     0 if bilinear == "cv2" else 1, core.ptr(xyz), core.ptr(center), core.ptr(kcrop), core.ptr(zmm),
                                                      dev.index, core.stream_ptr(dev)))
     if return_aux:
         return xyz, center, kcrop, zmm.view(torch.uint16)

@@ -371,14 +371,14 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
     dfr = torch.from_numpy(depth.view(np.int16)).to(dev).contiguous()        # uint16 bits
     bx = torch.from_numpy(boxes).to(dev)
     xyz = torch.empty(256, 3, device=dev)
-    t = timed(lambda: core.check(L.p6d_depth_crop_backproject(dfr.data_ptr(), 480, 640, bx.data_ptr(), 256, K1.data_ptr(), 224,
+    t = timed(lambda: core.check(L.p6d_depth_crop_backproject(dfr.data_ptr(), 480, 640, bx.data_ptr(), 256, K1.data_ptr(), 224, 0,
                                                               xyz.data_ptr(), None, None, None, dev.index, st)), 20)
     res.append({"kernel": "depth_crop_backproject (N1, config 4 ii): 480x640 uint16 frame, 256 boxes", "bound": "latency",
                 "boxes": 256, "us": round(t * 1e6, 2), "boxes_per_s": 256 / t})
     big = bx.repeat(4096, 1).contiguous()
     xyzb = torch.empty(big.shape[0], 3, device=dev)
     t = timed(lambda: core.check(L.p6d_depth_crop_backproject(dfr.data_ptr(), 480, 640, big.data_ptr(), big.shape[0], K1.data_ptr(),
-                                                              224, xyzb.data_ptr(), None, None, None, dev.index, st)))
+                                                              224, 0, xyzb.data_ptr(), None, None, None, dev.index, st)))
     hbm_row("depth_crop_backproject (N1), 2^20 boxes of one frame (frame stays in L2: 16 B box + 12 B out per row)",
             big.shape[0], 28, t)
 
@@ -423,6 +423,23 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
     torch.cuda.synchronize()
     res.append({"kernel": "PoseLoss forward+backward through autograd, B=32 (config 3)", "bound": "latency",
                 "us_per_step": (time.perf_counter() - t0) / 200 * 1e6})
+    # the same step captured in a CUDA graph (PoseLoss.capture): one cudaGraphLaunch per step
+    cap = crit.capture(rot, tr, gr, gtr)
+    for _ in range(20):
+        cap.replay()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(1000):
+        cap.replay()
+    torch.cuda.synchronize()
+    us_replay = (time.perf_counter() - t0) / 1000 * 1e6
+    t0 = time.perf_counter()
+    for _ in range(200):
+        cap(rot, tr, gr, gtr)
+    torch.cuda.synchronize()
+    res.append({"kernel": "PoseLoss.capture: the same step replayed from a CUDA graph, B=32", "bound": "latency",
+                "us_per_step": us_replay, "us_per_step_with_input_copies": (time.perf_counter() - t0) / 200 * 1e6,
+                "loss_equals_eager": bool(cap.loss.item() == crit(rot, tr, gr, gtr).item())})
     return res
 
 

@@ -36,7 +36,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define P6D_VERSION 2
+#define P6D_VERSION 3
 
 #define P6D_OK 0
 #define P6D_EINVAL (-1)   /* bad argument */
@@ -227,11 +227,14 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
  * followed by models/pose_net_rgbd_geometric.py:56-85, for B integer boxes (x,y,w,h) of ONE
  * uint16 depth frame [H,W] in millimetres and the frame's intrinsics K [3,3].
  *   xyz [B,3]; optional center [B,2] (crop-space bbox centre), kcrop [B,9], z_mm [B]
- *   (the resized crop's uint16 value under the centre).  Bilinear = cv2's generic path.
+ *   (the resized crop's uint16 value under the centre).
+ *   bilinear  which cv2.resize arithmetic for CV_16U to reproduce bit for bit:
+ *             0 = the pip wheel's default (IPP's ippiResizeLinear_16u: the call the reference makes),
+ *             1 = OpenCV's own C++ path (builds without IPP, cv2.ipp.setUseIPP(False)).
  * ------------------------------------------------------------------------------------- */
 int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes, int64_t B,
-                               const float* K, int img_size, float* xyz, float* center, float* kcrop,
-                               uint16_t* z_mm, int device, void* stream);
+                               const float* K, int img_size, int bilinear, float* xyz, float* center,
+                               float* kcrop, uint16_t* z_mm, int device, void* stream);
 
 /* 3-D -> 2-D projection of N model points for B poses:
  * utils/visualization.project_points (utils/visualization.py:8-32) in float64 --

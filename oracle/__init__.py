@@ -18,6 +18,8 @@ import ctypes as C
 import os
 import subprocess
 
+from fractions import Fraction
+
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -264,16 +266,78 @@ def depth_backproject(depth_raw, bbox_center, K, clamp_hi=223.0):
     return out
 
 
-def crop_depth_backproject(depth_u16, boxes, K, img_size=224):
+def _round_f32(fr):
+    """Exact rational -> nearest float32, ties to even (no double rounding)."""
+    c = np.float32(float(fr))
+    best = c
+    for cand in (np.nextafter(c, np.float32(-np.inf)), np.nextafter(c, np.float32(np.inf))):
+        dc, db = abs(Fraction(float(cand)) - fr), abs(Fraction(float(best)) - fr)
+        if dc < db or (dc == db and (int(cand.view(np.uint32)) & 1) == 0 and (int(best.view(np.uint32)) & 1) == 1):
+            best = cand
+    return best
+
+
+def fma32(x, y, z):
+    """float32 fused multiply-add, exactly rounded."""
+    return _round_f32(Fraction(float(x)) * Fraction(float(y)) + Fraction(float(z)))
+
+
+def resize_linear_u16(img, size=224, bilinear="cv2"):
+    """cv2.resize(img_u16, (size, size)) with INTER_LINEAR, restated for a whole square image (NumPy,
+    vectorised; used by the live pin in tests/test_live_pins.py).
+      bilinear="cv2"      what the pip wheel of OpenCV 4.x does for CV_16U by default -- the call the
+                          reference makes (data/dataset_rgbd.py:173): hal::resize hands 16-bit linear
+                          resizes to IPP (ippiResizeLinear_16u), whose arithmetic was identified by
+                          probing (oracle/VALIDATION.txt): source coordinate (d + 0.5) * (src / dst) - 0.5
+                          in float64, weight = float32(fraction), horizontal pass then vertical pass, each
+                          lerp as ONE float32 fma(b - a, w, a), round half to even, saturate.
+      bilinear="generic"  OpenCV's own C++ path (cv2.ipp.setUseIPP(False), cv2.setUseOptimized(False),
+                          or a build without IPP): coordinate rounded to float32, weights (1 - w, w),
+                          a * w0 + b * w1 with separate roundings; exact 2x down-scaling switches to
+                          INTER_AREA ((a + b + c + d + 2) >> 2)."""
+    f, d64 = np.float32, np.float64
+    img = np.asarray(img)
+    cs = img.shape[0]
+    assert img.shape == (cs, cs)
+    I = img.astype(f)
+    d = np.arange(size)
+    if bilinear == "cv2":
+        c = (d + 0.5) * (cs / float(size)) - 0.5
+        s = np.floor(c).astype(np.int64)
+        w = np.where(s < 0, 0.0, c - s).astype(f)
+        s0, s1 = np.clip(s, 0, cs - 1), np.clip(s + 1, 0, cs - 1)
+        lerp = lambda a, b, ww: (b.astype(d64) - a.astype(d64)).astype(f).astype(d64) * ww.astype(d64) + a.astype(d64)
+        hor = lerp(I[:, s0], I[:, s1], np.broadcast_to(w, (cs, size))).astype(f)
+        out = lerp(hor[s0], hor[s1], np.broadcast_to(w[:, None], (size, size))).astype(f)
+        return np.clip(np.rint(out), 0, 65535).astype(np.uint16)
+    if bilinear != "generic":
+        raise ValueError("bilinear must be 'cv2' or 'generic'")
+    if cs == 2 * size:
+        q = img.astype(np.int64)
+        return ((q[0::2, 0::2] + q[0::2, 1::2] + q[1::2, 0::2] + q[1::2, 1::2] + 2) >> 2).astype(np.uint16)
+    scale = 1.0 / (float(size) / float(cs))
+    v = ((d + 0.5) * scale - 0.5).astype(f)
+    s = np.floor(v).astype(np.int64)
+    w = (v - s.astype(f)).astype(f)
+    w = np.where((s < 0) | (s >= cs - 1), f(0), w).astype(f)
+    s = np.clip(s, 0, cs - 1)
+    s1 = np.minimum(s + 1, cs - 1)
+    w0 = (f(1) - w).astype(f)
+    hor = ((I[:, s] * w0).astype(f) + (I[:, s1] * w).astype(f)).astype(f)
+    out = ((hor[s] * w0[:, None]).astype(f) + (hor[s1] * w[:, None]).astype(f)).astype(f)
+    return np.clip(np.rint(out), 0, 65535).astype(np.uint16)
+
+
+def crop_depth_backproject(depth_u16, boxes, K, img_size=224, bilinear="cv2"):
     """N1 restatement (NumPy, per box): the crop geometry of LineMODDatasetRGBD.__getitem__
-    (data/dataset_rgbd.py:104-179, no augmentation), cv2.resize's generic INTER_LINEAR
-    path for uint16 evaluated at the single pixel the network reads, and the depth
-    back-projection of models/pose_net_rgbd_geometric.py:56-85.
+    (data/dataset_rgbd.py:104-179, no augmentation), cv2.resize's INTER_LINEAR for uint16
+    evaluated at the single pixel the network reads (`bilinear`: see resize_linear_u16 -- "cv2" is
+    the reference's default call, "generic" OpenCV without IPP), and the depth back-projection of
+    models/pose_net_rgbd_geometric.py:56-85.
     Python-int / float64 arithmetic where the reference uses Python scalars, float32 where
-    it uses NumPy float32 (NumPy 2 promotion rules).  cv2 (OpenCV 4.x, resize.cpp):
-    fx = float((dx + 0.5) * scale - 0.5), scale = 1 / (dst / src) in double; weights
-    (1 - fx, fx) in float; horizontal then vertical pass as float mul, mul, add;
-    saturate_cast<ushort>(rint)."""
+    it uses NumPy float32 (NumPy 2 promotion rules)."""
+    if bilinear not in ("cv2", "generic"):
+        raise ValueError("bilinear must be 'cv2' or 'generic'")
     f = np.float32
     depth = np.asarray(depth_u16)
     H, Wd = depth.shape
@@ -299,6 +363,12 @@ def crop_depth_backproject(depth_u16, boxes, K, img_size=224):
             s, w = cs - 1, f(0)
         return s, min(s + 1, cs - 1), f(f(1.0) - w), w
 
+    def axis_ipp(d, cs):
+        c = (d + 0.5) * (cs / float(img_size)) - 0.5          # float64
+        s = int(np.floor(c))
+        w = f(0) if s < 0 else f(c - s)
+        return min(max(s, 0), cs - 1), min(max(s + 1, 0), cs - 1), w
+
     for b in range(B):
         x, y, w, h = (int(v) for v in boxes[b])
         cgt = np.array([x + w / 2, y + h / 2], dtype=f)
@@ -317,11 +387,22 @@ def crop_depth_backproject(depth_u16, boxes, K, img_size=224):
                           [0, fy_ * scale32, f(f(cy_ + f(pad_t)) - f(y1)) * scale32], [0, 0, 1]], f)
         u = min(max(cr[0], f(0)), f(img_size - 1)); v = min(max(cr[1], f(0)), f(img_size - 1))
         ui, vi = min(max(int(u), 0), img_size - 1), min(max(int(v), 0), img_size - 1)
-        sx0, sx1, a0, a1 = axis(ui, cs)
-        sy0, sy1, b0, b1 = axis(vi, cs)
-        h0 = f(f(texel(sy0, sx0, x1, y1, pad_l, pad_t) * a0) + f(texel(sy0, sx1, x1, y1, pad_l, pad_t) * a1))
-        h1 = f(f(texel(sy1, sx0, x1, y1, pad_l, pad_t) * a0) + f(texel(sy1, sx1, x1, y1, pad_l, pad_t) * a1))
-        val = f(f(h0 * b0) + f(h1 * b1))
+        tx = lambda yy, xx: texel(yy, xx, x1, y1, pad_l, pad_t)
+        if bilinear == "cv2":
+            sx0, sx1, wx = axis_ipp(ui, cs)
+            sy0, sy1, wy = axis_ipp(vi, cs)
+            h0 = fma32(f(tx(sy0, sx1) - tx(sy0, sx0)), wx, tx(sy0, sx0))
+            h1 = fma32(f(tx(sy1, sx1) - tx(sy1, sx0)), wx, tx(sy1, sx0))
+            val = fma32(f(h1 - h0), wy, h0)
+        elif cs == 2 * img_size:          # generic path, exact 2x: INTER_AREA
+            q = [int(tx(2 * vi + dy, 2 * ui + dx)) for dy in (0, 1) for dx in (0, 1)]
+            val = f((sum(q) + 2) >> 2)
+        else:
+            sx0, sx1, a0, a1 = axis(ui, cs)
+            sy0, sy1, b0, b1 = axis(vi, cs)
+            h0 = f(f(tx(sy0, sx0) * a0) + f(tx(sy0, sx1) * a1))
+            h1 = f(f(tx(sy1, sx0) * a0) + f(tx(sy1, sx1) * a1))
+            val = f(f(h0 * b0) + f(h1 * b1))
         zi = int(np.clip(np.rint(val), 0, 65535))
         z_mm[b] = zi
         z = f(f(zi) / f(1000.0))

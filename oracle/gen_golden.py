@@ -324,6 +324,71 @@ def gen_crop():
     save("crop_backproject", **out)
 
 
+def gen_crop_ipp():
+    """N1, the case that matters: boxes whose centre pixel comes out DIFFERENT from cv2's default
+    (IPP) and from its generic C++ bilinear.  Candidates are found with the NumPy restatement
+    (oracle.crop_depth_backproject in both modes); the values stored are those of the reference's own
+    pipeline (LineMODDatasetRGBD.__getitem__ + PoseNetRGBDGeometric._compute_pinhole_translation) run
+    twice: with cv2 as the reference runs it (default: IPP on) and with cv2.ipp.setUseIPP(False)."""
+    import cv2, yaml
+    if REPO not in sys.path:
+        sys.path.append(REPO)
+    import oracle as O
+    from data.dataset_rgbd import LineMODDatasetRGBD
+    depth, _ = W.config4_frame(44, 8)
+    r = np.random.RandomState(45)
+    n_cand = 48000        # ~0.25 % of the boxes land on a pixel where the two arithmetics disagree
+    w = r.randint(30, 420, n_cand); h = r.randint(30, 420, n_cand)
+    x = (r.rand(n_cand) * 640 - 40).astype(np.int64); y = (r.rand(n_cand) * 480 - 40).astype(np.int64)
+    cand = np.stack([x, y, w, h], 1).astype(np.int32)
+    Kf = DEFAULT_K.astype(np.float32)
+    a = O.crop_depth_backproject(depth, cand, Kf, bilinear="cv2")["z_mm"].astype(np.int64)
+    b = O.crop_depth_backproject(depth, cand, Kf, bilinear="generic")["z_mm"].astype(np.int64)
+    differ = np.nonzero(a != b)[0]
+    same = np.nonzero(a == b)[0]
+    assert len(differ) >= 64, len(differ)
+    special = np.array([(300, 200, 374, 100),      # crop 448: exact 2x (generic path switches to INTER_AREA)
+                        (200, 150, 187, 100),      # crop 224: identity
+                        (10, 10, 20, 30),          # crop 36: x6.2 up-sampling
+                        (0, 0, 640, 480),          # whole frame, padded on all sides
+                        (-30, -20, 200, 180),      # starts outside the frame
+                        (500, 380, 300, 260)], np.int32)
+    boxes = np.concatenate([cand[differ[:64]], special, cand[same[:256 - 64 - len(special)]]]).astype(np.int32)
+    root = tempfile.mkdtemp()
+    d = os.path.join(root, "01")
+    os.makedirs(os.path.join(d, "rgb")); os.makedirs(os.path.join(d, "depth"))
+    cv2.imwrite(os.path.join(d, "rgb", "0000.png"), np.zeros((480, 640, 3), np.uint8))
+    cv2.imwrite(os.path.join(d, "depth", "0000.png"), depth)
+    K = [float(v) for v in DEFAULT_K.reshape(-1)]
+    eye = [1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0]
+    yaml.safe_dump({0: [{"obj_id": 1, "obj_bb": [int(v) for v in bx], "cam_R_m2c": eye, "cam_t_m2c": [0.0, 0.0, 800.0]}
+                        for bx in boxes]}, open(os.path.join(d, "gt.yml"), "w"))
+    yaml.safe_dump({0: {"cam_K": K, "depth_scale": 1.0}}, open(os.path.join(d, "info.yml"), "w"))
+    net = PoseNetRGBDGeometric.__new__(PoseNetRGBDGeometric)
+    out = {"seed": np.int64(44), "boxes": boxes, "K": Kf}      # the frame is W.config4_frame(seed, 8)[0]
+    for tag, ipp in (("cv2", True), ("generic", False)):
+        cv2.setUseOptimized(True)
+        cv2.ipp.setUseIPP(ipp)
+        ds = LineMODDatasetRGBD(root, mode="train", augment_bbox=False)
+        assert len(ds) == len(boxes)
+        centers, Ks, raws = [], [], []
+        for i in range(len(ds)):
+            _, _, depth_raw, _, _, _, c, Kc = ds[i]
+            centers.append(c.numpy()); Ks.append(Kc.numpy()); raws.append(depth_raw)
+        depth_raw = torch.stack(raws); c = T(np.stack(centers)); Kc = T(np.stack(Ks))
+        xyz = PoseNetRGBDGeometric._compute_pinhole_translation(net, depth_raw, c, Kc).numpy()
+        u = np.clip(np.clip(c.numpy()[:, 0], 0, 223).astype(np.int64), 0, 223)
+        v = np.clip(np.clip(c.numpy()[:, 1], 0, 223).astype(np.int64), 0, 223)
+        z_mm = np.rint(depth_raw.numpy()[np.arange(len(ds)), v, u] * 1000).astype(np.uint16)
+        out.update({f"{tag}_xyz": xyz, f"{tag}_z_mm": z_mm, f"{tag}_center": c.numpy(), f"{tag}_Kcrop": Kc.numpy()})
+    cv2.ipp.setUseIPP(True)
+    out["cv2_version"] = np.array(cv2.__version__)
+    n_diff = int((out["cv2_z_mm"] != out["generic_z_mm"]).sum())
+    assert n_diff >= 64, n_diff
+    print(f"crop_backproject_ipp: {n_diff} of {len(boxes)} boxes differ between cv2's default and its generic bilinear")
+    save("crop_backproject_ipp", **out)
+
+
 def gen_projection():
     """N4: utils/mesh_utils.load_mesh_corners (PLY -> 1/99 percentile box corners) and
     utils/visualization.project_points (scipy quaternion -> R, pinhole projection, int
@@ -355,7 +420,7 @@ def gen_projection():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_quat(); gen_eval(); gen_forward(); gen_forward_more(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_projection()
+    gen_quat(); gen_eval(); gen_forward(); gen_forward_more(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_crop_ipp(); gen_projection()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/gen_golden.py from {REF}\n"
                 f"torch {torch.__version__} cpu_capability {torch.backends.cpu.get_cpu_capability()} "

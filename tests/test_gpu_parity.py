@@ -416,6 +416,34 @@ def test_fused_geometric_training_step(pkg, cuda_dev, W):
     assert np.allclose(z.grad.cpu().numpy(), 3.0 * g["geodesic_b32_grad_z"], rtol=1e-5, atol=1e-7)
 
 
+def test_captured_training_step_equals_the_eager_step(pkg, cuda_dev, W):
+    """PoseLoss.capture: loss + gradients of config 3 replayed from a CUDA graph equal the eager
+    criterion(...).backward() bit for bit, for new inputs written into the static tensors, in both
+    forms (plain and forward_geometric)."""
+    crit = pkg.PoseLoss(1.0, 10.0, "geodesic")
+    c = W.config3(32, 6)
+    Tn = lambda x: T(x, cuda_dev)
+    step = crit.capture(Tn(c["rot_raw"]), Tn(c["gt_trans"]) + 0.01, Tn(c["gt_rot"]), Tn(c["gt_trans"]))
+    geo = crit.capture(Tn(c["rot_raw"]), Tn(c["z_pred"]), Tn(c["gt_rot"]), Tn(c["gt_trans"]),
+                       geometric=(Tn(c["bbox_center"]), Tn(c["K"])))
+    for seed in (6, 7, 8):
+        c = W.config3(32, seed)
+        rot = Tn(c["rot_raw"]).requires_grad_(True)
+        tr = (Tn(c["gt_trans"]) + 0.01 * seed).requires_grad_(True)
+        loss = crit(rot, tr, Tn(c["gt_rot"]), Tn(c["gt_trans"]))
+        loss.backward()
+        got = step(rot, tr, Tn(c["gt_rot"]), Tn(c["gt_trans"]))
+        assert got.item() == loss.item()
+        assert torch.equal(step.grad_rot, rot.grad) and torch.equal(step.grad_trans, tr.grad)
+        rot2 = Tn(c["rot_raw"]).requires_grad_(True)
+        z = Tn(c["z_pred"]).requires_grad_(True)
+        l2, trans = crit.forward_geometric(rot2, z, Tn(c["bbox_center"]), Tn(c["K"]), Tn(c["gt_rot"]), Tn(c["gt_trans"]))
+        l2.backward()
+        g2 = geo(rot2, z, Tn(c["bbox_center"]), Tn(c["K"]), Tn(c["gt_rot"]), Tn(c["gt_trans"]))
+        assert g2.item() == l2.item() and torch.equal(geo.translation, trans)
+        assert torch.equal(geo.grad_rot, rot2.grad) and torch.equal(geo.grad_z, z.grad)
+
+
 def test_pose_loss_weights_large_batch_and_no_grad(pkg, cuda_dev, W, oracle):
     g = load_golden("pose_loss_cfg3")
     a = T(g["rot_raw"], cuda_dev).requires_grad_(True)
@@ -524,19 +552,29 @@ def test_depth_crop_backproject_fused(pkg, cuda_dev, W, oracle):
     g = load_golden("crop_backproject")
     depth, boxes = W.config4_frame(int(g["seed"]), 256)
     K = torch.from_numpy(g["K"]).to(cuda_dev)
-    xyz, center, kcrop, zmm = pkg.depth_crop_backproject(torch.from_numpy(depth).to(cuda_dev), torch.from_numpy(boxes),
-                                                         K, return_aux=True)
-    assert same_bits(center.cpu().numpy(), g["generic_center"]) and same_bits(kcrop.cpu().numpy(), g["generic_Kcrop"])
-    assert np.array_equal(zmm.cpu().numpy(), g["generic_z_mm"])
-    assert same_bits(xyz.cpu().numpy(), g["generic_xyz"])                     # == reference dataset + model
-    assert np.abs(xyz.cpu().numpy()[:, 2] - g["optimized_xyz"][:, 2]).max() <= 0.001 + 1e-6   # IPP path: <= 1 mm
+    for mode, tag in (("cv2", "optimized"), ("generic", "generic")):     # == reference dataset + model, bit for bit
+        xyz, center, kcrop, zmm = pkg.depth_crop_backproject(torch.from_numpy(depth).to(cuda_dev), torch.from_numpy(boxes),
+                                                             K, return_aux=True, bilinear=mode)
+        assert same_bits(center.cpu().numpy(), g[f"{tag}_center"]) and same_bits(kcrop.cpu().numpy(), g[f"{tag}_Kcrop"])
+        assert np.array_equal(zmm.cpu().numpy(), g[f"{tag}_z_mm"])
+        assert same_bits(xyz.cpu().numpy(), g[f"{tag}_xyz"])
+    # the fixture whose pixels separate cv2's default (IPP) arithmetic from its generic one
+    gi = load_golden("crop_backproject_ipp")
+    frame, _ = W.config4_frame(int(gi["seed"]), 8)
+    for mode in ("cv2", "generic"):
+        xyz, center, kcrop, zmm = pkg.depth_crop_backproject(torch.from_numpy(frame).to(cuda_dev),
+                                                             torch.from_numpy(gi["boxes"]), K, return_aux=True, bilinear=mode)
+        assert np.array_equal(zmm.cpu().numpy(), gi[f"{mode}_z_mm"]), mode
+        assert same_bits(xyz.cpu().numpy(), gi[f"{mode}_xyz"]) and same_bits(center.cpu().numpy(), gi[f"{mode}_center"])
+    assert int((gi["cv2_z_mm"] != gi["generic_z_mm"]).sum()) >= 64
     # the fused result equals the two-step API (crop tensors + p6d_depth_backproject) as well
     # other seeds / frame sizes against the oracle, boxes partly outside the frame
     depth2, boxes2 = W.config4_frame(41, 300, hw=(360, 500))
     boxes2[:8, 0] -= 60; boxes2[8:16, 1] += 200
-    r = oracle.crop_depth_backproject(depth2, boxes2, g["K"])
-    xyz2 = pkg.depth_crop_backproject(depth2, boxes2, K)
-    assert same_bits(xyz2.cpu().numpy(), r["xyz"])
+    for mode in ("cv2", "generic"):
+        r = oracle.crop_depth_backproject(depth2, boxes2, g["K"], bilinear=mode)
+        xyz2 = pkg.depth_crop_backproject(depth2, boxes2, K, bilinear=mode)
+        assert same_bits(xyz2.cpu().numpy(), r["xyz"]), mode
     assert pkg.depth_crop_backproject(depth2, boxes2[:0], K).shape == (0, 3)
 
 

@@ -24,11 +24,25 @@ def test_library_exports_every_declared_symbol(pkg):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(pkg.core.EXPORTS) == declared
-    assert pkg.core.lib().p6d_version() == 2
+    assert pkg.core.lib().p6d_version() == pkg.core.P6D_VERSION == 3
     # the product library carries none of the development hooks
     assert not hasattr(L, "p6d_adds_timeline")
     blob = open(pkg.core.SO_PATH, "rb").read()
     assert b"P6D_ADDS_VARIANT" not in blob and b"P6D_DEBUG_SCAN_REPS" not in blob
+
+
+def test_measured_schedule_plans_fit_the_loops_this_source_compiles_to(pkg):
+    """csrc/sched_plan_*.json are tied to the instruction order ptxas emits (loop fingerprint): a
+    source change that makes ptxas emit another loop silently drops the build to the generic recipe
+    (-2 ... 3 % throughput).  The build log says which schedule every class got; with the committed
+    plans and this toolchain (nvcc 12.9) all three must be the measured plan.  A different toolchain
+    is a legitimate reason to see "recipe" here: re-run tools/sched_search.py then."""
+    from pathlib import Path
+    log = Path(pkg.core.SO_PATH).parent / "libp6d.sched.log"
+    if not log.exists():
+        pytest.skip("library built without the scheduling log (NOSCHED=1 or an older Makefile)")
+    got = dict(line.split() for line in log.read_text().splitlines() if line.strip())
+    assert got == {"n512": "plan", "n1024": "plan", "n2048": "plan"}, got
 
 
 def test_post_link_scheduling_pass_and_its_checks(pkg, tmp_path):

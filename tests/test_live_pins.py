@@ -119,6 +119,27 @@ def test_real_reference_when_reachable(oracle, eager, W):
         assert same_bits(a, b) and same_bits(a, c)
 
 
+@pytest.mark.parametrize("cs", [7, 36, 137, 224, 300, 447, 448, 449, 768])
+def test_cv2_resize_u16_arithmetic_of_this_machine(oracle, cs):
+    """cv2.resize on uint16 (data/dataset_rgbd.py:173) as THIS machine's OpenCV computes it: the
+    wheel's default goes through IPP (one float32 fma per lerp, float64 coordinate), with IPP switched
+    off through OpenCV's C++ code (separate roundings, INTER_AREA at exactly 2x).  Both restatements
+    (oracle.resize_linear_u16) must reproduce the whole 224x224 output."""
+    cv2 = pytest.importorskip("cv2")
+    if not (hasattr(cv2, "ipp") and cv2.ipp.useIPP()):
+        pytest.skip("this OpenCV build has no IPP: its default is the generic path")
+    r = np.random.RandomState(cs)
+    img = r.randint(0, 65535 if cs == 300 else 1500, (cs, cs)).astype(np.uint16)
+    try:
+        got = cv2.resize(img, (224, 224))
+        cv2.ipp.setUseIPP(False)
+        gen = cv2.resize(img, (224, 224))
+    finally:
+        cv2.ipp.setUseIPP(True)
+    assert np.array_equal(oracle.resize_linear_u16(img, 224, "cv2"), got), "cv2's default 16-bit bilinear changed"
+    assert np.array_equal(oracle.resize_linear_u16(img, 224, "generic"), gen), "cv2's generic 16-bit bilinear changed"
+
+
 # ------------------------------------------------------------------------------------------- GPU box
 @pytest.mark.gpu
 @pytest.mark.parametrize("n", [500, 1000, 2048])
@@ -176,3 +197,41 @@ def test_borderline_flags_and_the_resolver_hook(pkg, cuda_dev, eager, W):
     assert calls == [[0]]
     ref = eager.eval_poses({0: mesh}, {0: crit.diameters[0]}, pq, pt, gq, gt, obj)
     assert m["add_01d_acc"] == np.mean(ref[2].astype(np.float64)) * 100
+
+
+@pytest.mark.gpu
+def test_fused_crop_kernel_equals_cv2_run_on_this_box(pkg, cuda_dev, W):
+    """N1 against cv2 itself ON THE GPU BOX: for boxes inside the frame, the z_mm the kernel returns
+    equals the pixel of cv2.resize(crop) the reference would read, in cv2's default setting and with
+    IPP switched off."""
+    cv2 = pytest.importorskip("cv2")
+    depth, _ = W.config4_frame(46, 8)
+    r = np.random.RandomState(47)
+    n = 400
+    w = r.randint(30, 300, n); h = r.randint(30, 300, n)
+    x = (r.rand(n) * (640 - 1.2 * np.maximum(w, h)) + 0.1 * np.maximum(w, h)).astype(np.int64)
+    y = (r.rand(n) * (480 - 1.2 * np.maximum(w, h)) + 0.1 * np.maximum(w, h)).astype(np.int64)
+    boxes = np.stack([x, y, w, h], 1).astype(np.int32)
+    K = torch.tensor(pkg.DEFAULT_K, dtype=torch.float32, device=cuda_dev)
+    has_ipp = hasattr(cv2, "ipp") and cv2.ipp.useIPP()
+    for mode in ("cv2", "generic"):
+        if mode == "cv2" and not has_ipp:
+            continue
+        _, center, _, zmm = pkg.depth_crop_backproject(torch.from_numpy(depth).to(cuda_dev), torch.from_numpy(boxes), K,
+                                                       return_aux=True, bilinear=mode)
+        center, zmm = center.cpu().numpy(), zmm.cpu().numpy()
+        try:
+            if has_ipp:
+                cv2.ipp.setUseIPP(mode == "cv2")
+            for b in range(n):
+                bx, by, bw, bh = (int(v) for v in boxes[b])
+                size = max(bw, bh) * 1.2
+                x1, y1, cs = int(bx + bw / 2 - size / 2), int(by + bh / 2 - size / 2), int(size)
+                if x1 < 0 or y1 < 0 or x1 + cs > 640 or y1 + cs > 480:
+                    continue                       # padded boxes are covered by the golden fixtures
+                crop = cv2.resize(depth[y1:y1 + cs, x1:x1 + cs], (224, 224))
+                u, v = int(min(max(center[b, 0], 0), 223)), int(min(max(center[b, 1], 0), 223))
+                assert crop[v, u] == zmm[b], (mode, b, boxes[b])
+        finally:
+            if has_ipp:
+                cv2.ipp.setUseIPP(True)
