@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One launch of every secondary kernel at the sizes quoted in DESIGN.md (for ncu):
-   ncu --set full --clock-control none -k regex:'add_warp|pose_loss|pinhole|depth|add_backward|quat' -o gpurun_out/secondary python tools/profile_small.py"""
+   ncu --set full --clock-control none -k regex:'add_pose|pose_loss|pinhole|depth|add_backward|quat|tf32|synth|adds_cta' -o gpurun_out/secondary python tools/profile_small.py"""
 import importlib, os, sys, tempfile
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -49,5 +49,18 @@ o = T(np.array(W.LINEMOD_IDS, np.int64)[np.arange(32) % 13])
 x = a.requires_grad_(True); y = b.requires_grad_(True)
 crit(x, y, c, d, o).backward()
 crit._quat_to_mat(a)
+# loss form: ADDLoss.forward value in one launch (p6d_add_forward), B = 32 and B = 4096
+crit(a, b, c, d, o)
+a2, b2, c2, d2 = (T(x) for x in W.random_poses(4096, 6))
+crit(a2, b2, c2, d2, T(np.array(W.LINEMOD_IDS, np.int64)[np.arange(4096) % 13]))
+# config-5 hypothesis generator (p6d_synth_poses), one chunk of each kind
+for vi, var in enumerate(pkg.sweep.VARIANTS):
+    pkg.sweep.synth_block(1 << 18, 0, 5000, 0, vi, var, 0, dev)
+# the tcgen05 evidence kernel (opt-in, never on the product path): 2,048 poses of config 2
+pts2, dia2 = W.config2_meshes(2048)
+t2 = core.MeshTable(pts2, dia2, pkg.SYMMETRIC_OBJECT_IDS, dev)
+c2 = [T(x) for x in W.config2(2048)]
+out = torch.empty(2048, dtype=torch.float32, device=dev)
+core.check(core.lib().p6d_adds_tf32_eval(t2.handle, *(core.ptr(x) for x in c2), 2048, 3, core.ptr(out), 0, core.stream_ptr(dev)))
 torch.cuda.synchronize()
 print("profile_small done")
