@@ -257,6 +257,7 @@ extern "C" {
 int p6d_pinhole_fwd(const float* z, const float* uv, const float* K, int k_batched, int64_t B, float* out,
                     int device, void* stream) {
     if (B < 0 || (B > 0 && (!z || !uv || !K || !out))) { set_error("p6d_pinhole_fwd: bad arguments"); return P6D_EINVAL; }
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) { set_error("p6d_pinhole_fwd: bbox_center must be 8-byte aligned (float2 rows)"); return P6D_EINVAL; }
     if (B == 0) return P6D_OK;
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
@@ -271,6 +272,7 @@ int p6d_pinhole_fwd(const float* z, const float* uv, const float* K, int k_batch
 int p6d_pinhole_bwd(const float* grad_out, const float* uv, const float* K, int k_batched, int64_t B,
                     float* grad_z, int device, void* stream) {
     if (B < 0 || (B > 0 && (!grad_out || !uv || !K || !grad_z))) { set_error("p6d_pinhole_bwd: bad arguments"); return P6D_EINVAL; }
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) { set_error("p6d_pinhole_bwd: bbox_center must be 8-byte aligned (float2 rows)"); return P6D_EINVAL; }
     if (B == 0) return P6D_OK;
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
@@ -292,6 +294,10 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
         set_error("p6d_depth_backproject: clamp_hi=%g outside the %dx%d depth map", (double)clamp_hi, H, W);
         return P6D_EINVAL;
     }
+    if (reinterpret_cast<uintptr_t>(uv) & 7u) {
+        set_error("p6d_depth_backproject: bbox_center must be 8-byte aligned (float2 rows)");
+        return P6D_EINVAL;
+    }
     if (B == 0) return P6D_OK;
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
@@ -310,6 +316,10 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
     if (B < 0 || H < 1 || W < 1 || img_size < 1 || (bilinear != 0 && bilinear != 1) ||
         (B > 0 && (!depth || !boxes || !K || !xyz))) {
         set_error("p6d_depth_crop_backproject: bad arguments");
+        return P6D_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(boxes) & 15u) {
+        set_error("p6d_depth_crop_backproject: boxes must be 16-byte aligned (int4 rows)");
         return P6D_EINVAL;
     }
     if (B == 0) return P6D_OK;

@@ -53,13 +53,10 @@ __device__ __forceinline__ float sumsq4(const float* v) {
 // pt_row / gt_row / grad_t_row point at the 3 floats of row b.
 // FAST (large batches, geodesic mode only): see the header comment.
 template <bool FAST>
-__device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const float* pt_row,
-                                           const float* __restrict__ gq, const float* gt_row,
-                                           int64_t b, int64_t B, float wr, float wt, int mode,
-                                           float* __restrict__ grad_q, float* grad_t_row) {
+__device__ __forceinline__ RowOut loss_row(const float4 a4, const float* pt_row, const float4 c4, const float* gt_row,
+                                           int64_t B, float wr, float wt, int mode,
+                                           float* __restrict__ grad_q_row, float* grad_t_row) {
     RowOut o;
-    const float4 a4 = *reinterpret_cast<const float4*>(pq + 4 * b);
-    const float4 c4 = *reinterpret_cast<const float4*>(gq + 4 * b);
     const float a[4] = {a4.x, a4.y, a4.z, a4.w};
     const float c[4] = {c4.x, c4.y, c4.z, c4.w};
     float u[4], v[4];
@@ -152,7 +149,7 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
             gu[k] = wp * sp + wm * sm;
         }
     }
-    if (grad_q) {
+    if (grad_q_row) {
         float gdotu = 0.0f;
 #pragma unroll
         for (int k = 0; k < 4; ++k) gdotu = fmaf(gu[k], u[k], gdotu);
@@ -162,7 +159,7 @@ __device__ __forceinline__ RowOut loss_row(const float* __restrict__ pq, const f
         float* gp = reinterpret_cast<float*>(&g4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) gp[k] = scale * fmaf(-u[k], proj, gu[k]);
-        *reinterpret_cast<float4*>(grad_q + 4 * b) = g4;
+        *reinterpret_cast<float4*>(grad_q_row) = g4;
     }
     const float tscale = (float)((double)wt / (3.0 * (double)B));
 #pragma unroll
@@ -186,14 +183,17 @@ struct Geo {
     float* trans_out;    // [B,3] nullable: the translation the reference's model would return
 };
 
-template <bool FAST>
+template <bool FAST, bool GEO>
 __device__ __forceinline__ RowOut loss_row_any(const float* __restrict__ pq, const float* __restrict__ pt,
                                                const float* __restrict__ gq, const float* __restrict__ gt,
                                                int64_t b, int64_t B, float wr, float wt, int mode,
                                                float* __restrict__ grad_q, float* __restrict__ grad_t,
                                                const Geo& geo) {
-    if (!geo.z) return loss_row<FAST>(pq, pt + 3 * b, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q,
-                                grad_t ? grad_t + 3 * b : nullptr);
+    const float4 a4 = *reinterpret_cast<const float4*>(pq + 4 * b);
+    const float4 c4 = *reinterpret_cast<const float4*>(gq + 4 * b);
+    float* gq_row = grad_q ? grad_q + 4 * b : nullptr;
+    if (!GEO) return loss_row<FAST>(a4, pt + 3 * b, c4, gt + 3 * b, B, wr, wt, mode, gq_row,
+                                    grad_t ? grad_t + 3 * b : nullptr);
     const float* k = geo.K + (geo.k_batched ? 9 * b : 0);
     const float fx = __ldg(k + 0), cx = __ldg(k + 2), fy = __ldg(k + 4), cy = __ldg(k + 5);
     const float2 c = *reinterpret_cast<const float2*>(geo.uv + 2 * b);
@@ -201,7 +201,7 @@ __device__ __forceinline__ RowOut loss_row_any(const float* __restrict__ pq, con
     const float du = __fsub_rn(c.x, cx), dv = __fsub_rn(c.y, cy);
     float t3[3] = {__fdiv_rn(__fmul_rn(du, zz), fx), __fdiv_rn(__fmul_rn(dv, zz), fy), zz};
     float g3[3] = {0.0f, 0.0f, 0.0f};
-    const RowOut o = loss_row<FAST>(pq, t3, gq, gt + 3 * b, b, B, wr, wt, mode, grad_q, geo.grad_z ? g3 : nullptr);
+    const RowOut o = loss_row<FAST>(a4, t3, c4, gt + 3 * b, B, wr, wt, mode, gq_row, geo.grad_z ? g3 : nullptr);
     if (geo.trans_out) {
         geo.trans_out[3 * b + 0] = t3[0];
         geo.trans_out[3 * b + 1] = t3[1];
@@ -222,6 +222,7 @@ __device__ __forceinline__ void finish(float rot, float tr, float wr, float wt, 
 }
 
 // B <= SMALL_B: single CTA, ATen-ordered means
+template <bool GEO>
 __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq, const float* pt, const float* gq,
                                                                  const float* gt, int B, float wr, float wt,
                                                                  int mode, float* out, float* grad_q,
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq
     __shared__ float s_rot[SMALL_B];
     __shared__ float s_ad[3 * SMALL_B];
     for (int b = threadIdx.x; b < B; b += LOSS_T) {
-        const RowOut o = loss_row_any<false>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
+        const RowOut o = loss_row_any<false, GEO>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         s_rot[b] = o.rot;
         s_ad[3 * b] = o.ad[0];
         s_ad[3 * b + 1] = o.ad[1];
@@ -248,15 +249,18 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_small_kernel(const float* pq
 // Measured alternatives at 4 M rows (all slower than this shape, 91-94 us): prefetch.global.L1 of the
 // thread's next row (101 us), two rows per thread and trip (120 us, 80 registers), 6 CTAs per SM at
 // 40 registers (102 us, spills), shared-memory tile staging of the [B,3] rows (100 us).
-template <bool FAST>
-__global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq, const float* pt, const float* gq,
+#ifndef P6D_LOSS_MINB
+#define P6D_LOSS_MINB 4     // CTAs per SM the register budget is sized for
+#endif
+template <bool FAST, bool GEO>
+__global__ void __launch_bounds__(LOSS_T, P6D_LOSS_MINB) pose_loss_large_kernel(const float* pq, const float* pt, const float* gq,
                                                                  const float* gt, int64_t B, float wr, float wt,
                                                                  int mode, float* out, float* grad_q,
                                                                  float* grad_t, Workspace* ws, Geo geo) {
     double rs = 0.0, ts = 0.0;
     // (prefetching the next row of the thread with prefetch.global.L1 was tried: 10 % slower)
     for (int64_t b = (int64_t)blockIdx.x * LOSS_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * LOSS_T) {
-        const RowOut o = loss_row_any<FAST>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
+        const RowOut o = loss_row_any<FAST, GEO>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, geo);
         rs += (double)o.rot;
         ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
     }
@@ -290,6 +294,118 @@ __global__ void __launch_bounds__(LOSS_T) pose_loss_large_kernel(const float* pq
     }
 }
 
+// B > SMALL_B, plain PoseLoss, 16-byte aligned inputs: the same rows STREAMED through shared memory.
+// The grid-stride kernel above has at most one row per thread in flight (56 B x 1,024 threads = 57 KB
+// per SM), which is less than HBM latency x bandwidth asks for (ncu: stall "long scoreboard" 10 warps
+// per issue cycle, DRAM 54 % busy).  Here one thread per CTA issues TMA bulk copies
+// (cp.async.bulk, SASS UBLKCP) of whole 256-row tiles -- [256,4] + [256,4] + [256,3] + [256,3] floats =
+// 14 KB -- into a ring of STREAM_STAGES stages, each with its own mbarrier, so STAGES x 14 KB x CTAs/SM
+// are in flight independent of what the warps are doing; the warps read their row out of shared memory
+// (float4 / stride-3 scalars: conflict-free), hand the stage back with one __syncthreads and compute.
+constexpr int STREAM_STAGES = 3;
+constexpr int STREAM_TILE = LOSS_T;                                  // rows per tile = threads
+constexpr int STREAM_STAGE_FLOATS = STREAM_TILE * (4 + 4 + 3 + 3);   // pq | gq | pt | gt
+constexpr int STREAM_CTAS_PER_SM = 4;
+
+template <bool FAST>
+__global__ void __launch_bounds__(LOSS_T, STREAM_CTAS_PER_SM) pose_loss_stream_kernel(
+    const float* __restrict__ pq, const float* __restrict__ pt, const float* __restrict__ gq,
+    const float* __restrict__ gt, int64_t B, float wr, float wt, int mode, float* out, float* __restrict__ grad_q,
+    float* __restrict__ grad_t, Workspace* ws) {
+    extern __shared__ __align__(128) float s_ring[];
+    __shared__ uint64_t s_full[STREAM_STAGES];
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = B / STREAM_TILE;          // full tiles; the ragged tail is read directly
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STREAM_STAGES; ++s) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t tile, int stage) {      // thread 0 only
+        float* dst = s_ring + stage * STREAM_STAGE_FLOATS;
+        const int64_t r0 = tile * STREAM_TILE;
+        mbar_arrive_expect_tx(&s_full[stage], STREAM_STAGE_FLOATS * sizeof(float));
+        tma_bulk_g2s(dst, pq + 4 * r0, STREAM_TILE * 16, &s_full[stage]);
+        tma_bulk_g2s(dst + STREAM_TILE * 4, gq + 4 * r0, STREAM_TILE * 16, &s_full[stage]);
+        tma_bulk_g2s(dst + STREAM_TILE * 8, pt + 3 * r0, STREAM_TILE * 12, &s_full[stage]);
+        tma_bulk_g2s(dst + STREAM_TILE * 11, gt + 3 * r0, STREAM_TILE * 12, &s_full[stage]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STREAM_STAGES; ++s) {
+            const int64_t tile = blockIdx.x + static_cast<int64_t>(s) * gridDim.x;
+            if (tile < n_tiles) issue(tile, s);
+        }
+    }
+    double rs = 0.0, ts = 0.0;
+    int k = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const int stage = k % STREAM_STAGES;
+        mbar_wait(&s_full[stage], (k / STREAM_STAGES) & 1);
+        const float* src = s_ring + stage * STREAM_STAGE_FLOATS;
+        const float4 a4 = reinterpret_cast<const float4*>(src)[tid];
+        const float4 c4 = reinterpret_cast<const float4*>(src + STREAM_TILE * 4)[tid];
+        float t3[3], g3[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            t3[c] = src[STREAM_TILE * 8 + 3 * tid + c];
+            g3[c] = src[STREAM_TILE * 11 + 3 * tid + c];
+        }
+        __syncthreads();                              // every thread holds its row: the stage is free
+        if (tid == 0) {
+            const int64_t next = tile + static_cast<int64_t>(STREAM_STAGES) * gridDim.x;
+            if (next < n_tiles) {
+                fence_proxy_async();
+                issue(next, stage);
+            }
+        }
+        const int64_t b = tile * STREAM_TILE + tid;
+        const RowOut o = loss_row<FAST>(a4, t3, c4, g3, B, wr, wt, mode, grad_q ? grad_q + 4 * b : nullptr,
+                                        grad_t ? grad_t + 3 * b : nullptr);
+        rs += (double)o.rot;
+        ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
+    }
+    // ragged tail (< 256 rows): CTA 0, straight from global memory
+    if (blockIdx.x == 0) {
+        const int64_t b = n_tiles * STREAM_TILE + tid;
+        if (b < B) {
+            Geo none{};
+            const RowOut o = loss_row_any<FAST, false>(pq, pt, gq, gt, b, B, wr, wt, mode, grad_q, grad_t, none);
+            rs += (double)o.rot;
+            ts += ((double)o.ad[0] + (double)o.ad[1]) + (double)o.ad[2];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rs += __shfl_xor_sync(0xffffffffu, rs, o);
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+    }
+    __shared__ double s_r[LOSS_T / 32], s_t[LOSS_T / 32];
+    __shared__ bool s_last;
+    const int w = tid >> 5, lane = tid & 31;
+    if (lane == 0) { s_r[w] = rs; s_t[w] = ts; }
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0, t = 0.0;
+        for (int i = 0; i < LOSS_T / 32; ++i) { r += s_r[i]; t += s_t[i]; }
+        atomicAdd(&ws->rot_sum, r);
+        atomicAdd(&ws->trans_sum, t);
+        __threadfence();
+        const unsigned long long done = atomicAdd(&ws->blocks_done, 1ull);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        const double r = atomicAdd(&ws->rot_sum, 0.0), t = atomicAdd(&ws->trans_sum, 0.0);
+        finish((float)(r / (double)B), (float)(t / (3.0 * (double)B)), wr, wt, out);
+        ws->rot_sum = 0.0;
+        ws->trans_sum = 0.0;
+        ws->blocks_done = 0ull;
+    }
+}
+
 }  // namespace p6d
 
 using namespace p6d;
@@ -304,9 +420,10 @@ static int launch_pose_loss(const float* pq, const float* pt, const float* gq, c
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool g = geo.z != nullptr;
     if (B <= SMALL_B) {
-        pose_loss_small_kernel<<<1, LOSS_T, 0, st>>>(pq, pt, gq, gt, (int)B, rot_weight, trans_weight, mode, out,
-                                                     grad_q, grad_t, geo);
+        auto k = g ? pose_loss_small_kernel<true> : pose_loss_small_kernel<false>;
+        k<<<1, LOSS_T, 0, st>>>(pq, pt, gq, gt, (int)B, rot_weight, trans_weight, mode, out, grad_q, grad_t, geo);
     } else {
         if (!workspace) { set_error("pose loss: workspace required for B > %d", SMALL_B); return P6D_EINVAL; }
         int sms = 0;
@@ -316,14 +433,24 @@ static int launch_pose_loss(const float* pq, const float* pt, const float* gq, c
         if (blocks > cap) blocks = cap;
         // geodesic: FAST row (nothing is bit-exact at this size anyway); quaternion-L1: exact row, because
         // its sub-gradient is a sign pattern that a 1-ulp change of u - v could flip
-        if (mode == 0)
-            pose_loss_large_kernel<true><<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
-                                                                              mode, out, grad_q, grad_t,
-                                                                              static_cast<Workspace*>(workspace), geo);
-        else
-            pose_loss_large_kernel<false><<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight,
-                                                                               mode, out, grad_q, grad_t,
-                                                                               static_cast<Workspace*>(workspace), geo);
+        const bool aligned = ((reinterpret_cast<uintptr_t>(pq) | reinterpret_cast<uintptr_t>(gq) |
+                               reinterpret_cast<uintptr_t>(pt) | reinterpret_cast<uintptr_t>(gt)) & 15u) == 0;
+        if (!g && aligned) {
+            const size_t smem = static_cast<size_t>(STREAM_STAGES) * STREAM_STAGE_FLOATS * sizeof(float);
+            auto k = mode == 0 ? pose_loss_stream_kernel<true> : pose_loss_stream_kernel<false>;
+            static_assert(STREAM_STAGES * STREAM_STAGE_FLOATS * sizeof(float) + 512 <= 48 * 1024,
+                          "the ring must fit the default dynamic shared memory limit (no opt-in attribute is set)");
+            int64_t grid = static_cast<int64_t>(sms) * STREAM_CTAS_PER_SM;
+            const int64_t n_tiles = B / STREAM_TILE;
+            if (grid > n_tiles) grid = n_tiles > 0 ? n_tiles : 1;
+            k<<<(unsigned)grid, LOSS_T, smem, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight, mode, out, grad_q, grad_t,
+                                                    static_cast<Workspace*>(workspace));
+        } else {
+            auto k = mode == 0 ? (g ? pose_loss_large_kernel<true, true> : pose_loss_large_kernel<true, false>)
+                               : (g ? pose_loss_large_kernel<false, true> : pose_loss_large_kernel<false, false>);
+            k<<<(unsigned)blocks, LOSS_T, 0, st>>>(pq, pt, gq, gt, B, rot_weight, trans_weight, mode, out, grad_q, grad_t,
+                                                   static_cast<Workspace*>(workspace), geo);
+        }
     }
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;
@@ -334,6 +461,10 @@ int p6d_pose_loss_fwd_bwd(const float* pq, const float* pt, const float* gq, con
                           float* grad_t, void* workspace, int device, void* stream) {
     if (B <= 0 || !pq || !pt || !gq || !gt || !out || (mode != 0 && mode != 1)) {
         set_error("p6d_pose_loss_fwd_bwd: bad arguments (B=%lld, mode=%d)", (long long)B, mode);
+        return P6D_EINVAL;
+    }
+    if (((reinterpret_cast<uintptr_t>(pq) | reinterpret_cast<uintptr_t>(gq) | reinterpret_cast<uintptr_t>(grad_q)) & 15u) != 0) {
+        set_error("p6d_pose_loss_fwd_bwd: pred_rot, gt_rot and grad_q must be 16-byte aligned (float4 rows)");
         return P6D_EINVAL;
     }
     Geo geo{};
@@ -347,6 +478,11 @@ int p6d_pose_loss_pinhole_fwd_bwd(const float* pq, const float* z, const float* 
                                   float* trans_out, void* workspace, int device, void* stream) {
     if (B <= 0 || !pq || !z || !uv || !K || !gq || !gt || !out || (mode != 0 && mode != 1)) {
         set_error("p6d_pose_loss_pinhole_fwd_bwd: bad arguments (B=%lld, mode=%d)", (long long)B, mode);
+        return P6D_EINVAL;
+    }
+    if (((reinterpret_cast<uintptr_t>(pq) | reinterpret_cast<uintptr_t>(gq) | reinterpret_cast<uintptr_t>(grad_q)) & 15u) != 0 ||
+        (reinterpret_cast<uintptr_t>(uv) & 7u) != 0) {
+        set_error("p6d_pose_loss_pinhole_fwd_bwd: pred_rot, gt_rot, grad_q must be 16-byte and bbox_center 8-byte aligned");
         return P6D_EINVAL;
     }
     Geo geo{z, uv, K, k_batched, grad_z, trans_out};

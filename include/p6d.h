@@ -15,7 +15,8 @@
  *   - unless the name ends in _host, data pointers are DEVICE pointers on the device the
  *     mesh table (or, for table-less calls, the `device` argument) belongs to, float32
  *     contiguous, quaternions scalar-last [x,y,z,w], translations in metres, K row-major
- *     3x3; the caller owns every buffer;
+ *     3x3; the caller owns every buffer; [B,4] float rows and int32 boxes must be 16-byte aligned,
+ *     [B,2] rows 8-byte aligned (vector loads; a misaligned pointer is refused with P6D_EINVAL);
  *   - there is no CPU fallback: without a CUDA device every compute entry fails with
  *     P6D_ECUDA;
  *   - threading: the table-less entries and p6d_add_eval / p6d_add_backward may be called

@@ -471,6 +471,38 @@ def test_pose_loss_weights_large_batch_and_no_grad(pkg, cuda_dev, W, oracle):
         assert not l2.requires_grad and l2.item() == l.item()      # workspace left clean, deterministic
 
 
+def test_large_pose_loss_streamed_and_direct_kernels_agree_and_misalignment_is_refused(pkg, cuda_dev, W, oracle):
+    """B > 2048: 16-byte aligned inputs go through the TMA-streamed kernel, anything else through the
+    grid-stride kernel; both against the oracle.  Misaligned float4 rows are an error, not a fault."""
+    core = pkg.core
+    L = core.lib()
+    B = 30000 + 77                                           # 117 full tiles + a ragged tail
+    pq, pt, gq, gt = W.random_poses(B, 35, rot_sigma=0.3, trans_sigma=0.05)
+    o = oracle.pose_loss(pq, pt, gq, gt, 1.0, 10.0, "geodesic")
+    ws = torch.zeros(64, dtype=torch.uint8, device=cuda_dev)
+    dq, dgq = T(pq, cuda_dev), T(gq, cuda_dev)
+    pad = torch.zeros(3 * B + 8, dtype=torch.float32, device=cuda_dev)
+    res = {}
+    for name, off in (("streamed", 0), ("direct", 1)):      # off = 1 float: [B,3] rows only 4-byte aligned
+        dpt = pad[off:off + 3 * B].copy_(T(pt, cuda_dev).reshape(-1))
+        dgt = torch.zeros(3 * B + 8, dtype=torch.float32, device=cuda_dev)[off:off + 3 * B].copy_(T(gt, cuda_dev).reshape(-1))
+        assert (dpt.data_ptr() % 16 == 0) == (off == 0)
+        out = torch.empty(3, device=cuda_dev); g1 = torch.empty(B, 4, device=cuda_dev); g2 = torch.empty(3 * B, device=cuda_dev)
+        core.check(L.p6d_pose_loss_fwd_bwd(dq.data_ptr(), dpt.data_ptr(), dgq.data_ptr(), dgt.data_ptr(), B, 1.0, 10.0, 0,
+                                           out.data_ptr(), g1.data_ptr(), g2.data_ptr(), ws.data_ptr(), cuda_dev.index,
+                                           core.stream_ptr(cuda_dev)))
+        torch.cuda.synchronize()
+        res[name] = (out.cpu().numpy(), g1.cpu().numpy(), g2.cpu().numpy().reshape(B, 3))
+        assert abs(res[name][0][0] - float(o["loss"])) <= 1e-5 * float(o["loss"]), name
+        sc = np.maximum(np.abs(o["grad_q"]).max(1, keepdims=True), 1e-30)
+        assert np.all(np.abs(res[name][1] - o["grad_q"]) <= 1e-5 * sc), name
+        assert same_bits(res[name][2], o["grad_t"]), name
+    assert same_bits(res["streamed"][1], res["direct"][1])      # same row arithmetic in both kernels
+    rc = L.p6d_pose_loss_fwd_bwd(dq.data_ptr() + 4, pad.data_ptr(), dgq.data_ptr(), pad.data_ptr(), 16, 1.0, 10.0, 0,
+                                 ws.data_ptr(), None, None, ws.data_ptr(), cuda_dev.index, core.stream_ptr(cuda_dev))
+    assert rc == core.P6D_EINVAL and b"16-byte aligned" in L.p6d_last_error()
+
+
 # ------------------------------------------------------------------ geometric translation
 def test_pinhole_forward_backward(pkg, cuda_dev):
     g = load_golden("pinhole")

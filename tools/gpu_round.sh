@@ -11,9 +11,9 @@ for step in "$@"; do
     smoke)  timeout 200 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_smoke.log; tail -4 $OUT/${TAG}_smoke.log ;;
     bench)  timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"; tail -3 $OUT/${TAG}_bench.err; head -c 1500 $OUT/${TAG}_bench.json ;;
     ref)    timeout 300 python bench.py --impl reference > $OUT/${TAG}_ref.json 2> $OUT/${TAG}_ref.err; echo "ref rc=$?"; head -c 600 $OUT/${TAG}_ref.json ;;
-    search2048) timeout 700 python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi256ELi8ELi2ELi0ELi0EE 2 2048 65536 ${SEARCH_S:-420} 6d-pose-estimation_b200/csrc/sched_plan_n2048.json > $OUT/${TAG}_search2048.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search2048.log; tail -4 $OUT/${TAG}_search2048.log | cut -c1-600 ;;
-    search1024) timeout 500 python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi256ELi4ELi4ELi0ELi0EE 1 1000 262144 ${SEARCH_S:-240} 6d-pose-estimation_b200/csrc/sched_plan_n1024.json 3,0 > $OUT/${TAG}_search1024.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search1024.log; tail -4 $OUT/${TAG}_search1024.log | cut -c1-600 ;;
-    search512)  timeout 500 python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi128ELi4ELi8ELi0ELi0EE 0 500 1048576 ${SEARCH_S:-240} 6d-pose-estimation_b200/csrc/sched_plan_n512.json 8,0 > $OUT/${TAG}_search512.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search512.log; tail -4 $OUT/${TAG}_search512.log | cut -c1-600 ;;
+    search2048) SEARCH_CHECKPOINT=$OUT/${TAG}_plan2048.json timeout $(( ${SEARCH_S:-420} + 240 )) python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi256ELi8ELi2ELi0ELi0EE 2 2048 65536 ${SEARCH_S:-420} 6d-pose-estimation_b200/csrc/sched_plan_n2048.json > $OUT/${TAG}_search2048.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search2048.log; tail -4 $OUT/${TAG}_search2048.log | cut -c1-600 ;;
+    search1024) SEARCH_CHECKPOINT=$OUT/${TAG}_plan1024.json timeout $(( ${SEARCH_S:-240} + 240 )) python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi256ELi4ELi4ELi0ELi0EE 1 1000 262144 ${SEARCH_S:-240} 6d-pose-estimation_b200/csrc/sched_plan_n1024.json 3,0 > $OUT/${TAG}_search1024.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search1024.log; tail -4 $OUT/${TAG}_search1024.log | cut -c1-600 ;;
+    search512)  SEARCH_CHECKPOINT=$OUT/${TAG}_plan512.json timeout $(( ${SEARCH_S:-240} + 240 )) python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi128ELi4ELi8ELi0ELi0EE 0 500 1048576 ${SEARCH_S:-240} 6d-pose-estimation_b200/csrc/sched_plan_n512.json 8,0 > $OUT/${TAG}_search512.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search512.log; tail -4 $OUT/${TAG}_search512.log | cut -c1-600 ;;
     ncu)    # launch list + full capture of the headline kernel + the secondary kernels (only after bench exited 0)
             BARGS="--no-sweep --no-secondary --no-cpu-baseline --no-microbench"
             timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 $BARGS > $OUT/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?"

@@ -151,6 +151,11 @@ while time.time() < t_end:
         best_t, order, yields = t, cand_o, cand_y
         accepted += 1
         print(f"{evals:4d} {what:28s} -> {best_t:.3f} ms", flush=True)
+        if os.environ.get("SEARCH_CHECKPOINT"):     # survive a kill: the best plan so far, rewritten on every accepted move
+            with open(os.environ["SEARCH_CHECKPOINT"], "w") as fh:
+                json.dump({"kernel": kernel, "evals": evals, "accepted": accepted, "ptxas_ms": t_ptxas, "best_ms": best_t,
+                           "packed_stall": 1, "order": order, "yield_mask": "".join(str(y) for y in yields),
+                           "movable": [k for k in range(n) if S.movable(body[k])], "loop_fingerprint": S.fingerprint(body)}, fh)
 print(json.dumps({"kernel": kernel, "found_by": f"tools/sched_search.py: {evals} timed candidates on B200 ({poses} poses, N={npts}), "
                                                "hill climbing over yield bits and slot moves of the minima",
                   "evals": evals, "accepted": accepted, "ptxas_ms": t_ptxas, "best_ms": best_t, "packed_stall": 1,
