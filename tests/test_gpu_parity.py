@@ -541,8 +541,9 @@ def test_sweep_is_invariant_to_the_number_of_ranks_and_matches_oracle(pkg, cuda_
     dia = {0: 0.102, 9: 0.1646, 12: 0.278}
     n, chunk = 3000, 1024
     full, launches, check = pkg.evaluate_sweep(pts, dia, cuda_dev, n, chunk=chunk, seed=77, check_n=64)
-    # per block 3 chunks x (generate + evaluate) and one translation launch per chunk of the two geometric variants
-    assert launches == 3 * 3 * (4 * 2 + 2) and int(full.valid.sum()) == 3 * 4 * n
+    # per block 3 chunks x (generate + evaluate + chunk totals) and one translation launch per chunk of the two
+    # geometric variants
+    assert launches == 3 * 3 * (4 * 3 + 2) and int(full.valid.sum()) == 3 * 4 * n
     for world in (2, 3):
         parts = [pkg.evaluate_sweep(pts, dia, cuda_dev, n, chunk=chunk, seed=77, rank=r, world=world)[0]
                  for r in range(world)]
