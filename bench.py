@@ -338,7 +338,7 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
         r.update(extra)
         res.append(r)
 
-    n = 1 << 22
+    n = 1 << 24            # ~1.4 GB per kernel: the fixed cost of a launch + event pair (2-4 us) stays below 1-2 %
     g = torch.Generator(device=dev); g.manual_seed(7)
     rnd = lambda *shape: torch.randn(*shape, generator=g, device=dev)
     pq, gq, pt, gt = rnd(n, 4), rnd(n, 4), rnd(n, 3), rnd(n, 3)
@@ -356,7 +356,8 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
     hbm_row("pinhole_fwd (d1), K [B,3,3]", n, 60, t)
     t = timed(lambda: core.check(L.p6d_pinhole_fwd(z.data_ptr(), uv.data_ptr(), K1.data_ptr(), 0, n, o.data_ptr(), dev.index, st)))
     hbm_row("pinhole_fwd (d1), shared K [3,3]", n, 24, t)
-    m = 1 << 20
+    del pq, gq, pt, gt, g1, g2
+    m = 1 << 22
     d8 = torch.rand(m, 8, 8, device=dev) * 1.5
     uv8 = torch.rand(m, 2, device=dev) * 8
     o8 = torch.empty(m, 3, device=dev)
@@ -391,6 +392,8 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
         r.update(extra)
         res.append(r)
 
+    del d8, uv8, o8, K, z, uv, o
+    m = 1 << 20
     pts = {0: W.sphere_mesh(1000, 0.102, 100)}
     table = core.MeshTable(pts, {0: 0.102}, pkg.SYMMETRIC_OBJECT_IDS, dev)
     obj = torch.zeros(m, dtype=torch.int64, device=dev)

@@ -35,6 +35,16 @@ def one(lib):
         ref = O.add_eval(O.MeshTable(pts, {0: 0.102}), qb[:2048].cpu().numpy(), tb[:2048].cpu().numpy(), qa[:2048].cpu().numpy(),
                          ta[:2048].cpu().numpy(), np.zeros(2048, np.int64), want_adds=False, n_threads=O.max_threads())[0]
         out[f"add_n{n}"] = {"Mposes_s": m / t / 1e6, "bits_ok": bool(np.array_equal(add.view(np.uint32), ref.view(np.uint32)))}
+    import hashlib
+    for npts, Bn in ((500, 1 << 20), (1000, 1 << 18), (2048, 1 << 16)):
+        pts = {9: W.box_mesh(npts, (0.1, 0.12, 0.05), 200 + npts)}
+        tb_ = core.MeshTable(pts, {9: 0.1646}, pkg.SYMMETRIC_OBJECT_IDS, dev)
+        ob = torch.full((Bn,), 9, dtype=torch.int64, device=dev)
+        t = timed(lambda: tb_.evaluate(qb[:Bn], tb[:Bn], qa[:Bn], ta[:Bn], ob, want_adds=True), 5)
+        packed = tb_.evaluate(qb[:Bn], tb[:Bn], qa[:Bn], ta[:Bn], ob, want_adds=True)[4]
+        out[f"adds_n{npts}"] = {"Mposes_s": Bn / t / 1e6, "frac_nominal": Bn * 8 * npts * npts / t / 74.45e12,
+                                "md5": hashlib.md5(packed[:10 * Bn].cpu().numpy().tobytes()).hexdigest()[:8],
+                                "sched": tb_.schedule_state()}
     n = 1 << 22
     pq, gq, pt, gt = rnd(n, 4), rnd(n, 4), rnd(n, 3), rnd(n, 3)
     o3 = torch.empty(3, device=dev); g1 = torch.empty_like(pq); g2 = torch.empty_like(pt)
