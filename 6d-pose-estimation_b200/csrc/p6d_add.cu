@@ -455,11 +455,7 @@ static const AddsVariant g_adds_variants[] = {
     {"T128_K4_B8_U2", 128, (const void*)adds_cta_kernel<128, 4, 8, 2, 0>},
     // 3-5: software-pipelined minima (U = 0), re-scheduled after linking by csrc/sass_sched.py
     {"T256_K8_B2_D", 256, (const void*)adds_cta_kernel<256, 8, 2, 0, 0>},
-#ifdef P6D_K8_MID      // experiment: 8 pred points per thread for 513..1024-point meshes as well
-    {"T128_K8_B4_D", 128, (const void*)adds_cta_kernel<128, 8, 4, 0, 0>},
-#else
     {"T256_K4_B4_D", 256, (const void*)adds_cta_kernel<256, 4, 4, 0, 0>},
-#endif
     {"T128_K4_B8_D", 128, (const void*)adds_cta_kernel<128, 4, 8, 0, 0>},
     // 6-8: loss form (ADDLoss.forward): shapes 0-2 + per-sample value + grouped sum by the last CTA
     {"T512_K4_B2_U2_loss", 512, (const void*)adds_cta_kernel<512, 4, 2, 2, 1>},

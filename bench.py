@@ -319,12 +319,17 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
     L, st = core.lib(), core.stream_ptr(dev)
 
     def timed(fn, reps=10):
+        """Best CUDA-event time of one call.  A ~100 us device-side spin is queued first, so that the start
+        event, the kernel and the stop event are all in the queue before the GPU reaches them -- otherwise the
+        10-15 us the host needs to get from `record` through ctypes to the launch are counted as kernel time
+        (ncu: 55 us for a kernel that timed 71 us that way)."""
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
         best = 1e30
         for _ in range(reps):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(200_000)
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) * 1e-3)
         return best
