@@ -88,8 +88,8 @@ int p6d_adds_schedule(void);
 int p6d_adds_schedule_state(const p6d_mesh_table* table, int* built_relaid, int* runtime_state);
 int p6d_adds_selfcheck(const p6d_mesh_table* table, int64_t n_poses, int64_t* mismatches);
 
-/* All 2^32 float32 bit patterns through the packed square root of kernel (a) and through
- * sqrt.rn.f32; mismatches must come back 0. */
+/* All 2^32 float32 bit patterns through the packed square roots of kernel (a) (two-way and
+ * four-way form) and through sqrt.rn.f32; mismatches must come back 0. */
 int p6d_selftest_sqrt2(int device, int64_t* mismatches);
 
 /* ---------------------------------------------------------------------------------------

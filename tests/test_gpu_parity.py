@@ -182,6 +182,31 @@ def test_add_only_kernel_every_row_shape(pkg, cuda_dev, W, oracle):
         assert np.array_equal(hit.cpu().numpy(), ref[2]) and valid.cpu().numpy().all()
 
 
+@pytest.mark.parametrize("n", [5, 96, 500, 1000, 1001, 2048])
+def test_add_only_kernel_single_mesh_table(pkg, cuda_dev, W, oracle, n):
+    """Kernel (a) with a table that holds ONE mesh takes the barrier-free form (the mesh is staged once
+    per CTA and the warps never meet again): same bits, poses with another id are skipped, exact zeros
+    (the repaired branch of the four-way square root), NaN and a ragged last round."""
+    pts = {3: W.sphere_mesh(n, 0.12, 900 + n)}
+    dia = {3: 0.12}
+    B = 2053
+    pq, pt, gq, gt = W.random_poses(B, 50 + n, rot_sigma=np.geomspace(0.005, 0.3, B))
+    obj = np.full(B, 3, np.int64)
+    obj[5] = 2; obj[6] = 77; obj[7] = -4
+    pq[20] = gq[20]; pt[20] = gt[20]                  # every distance exactly 0
+    pt[21, 2] = np.nan
+    pq[22] *= 1e-3                                    # tiny rotation entries: denormal-range squares for some points
+    table = pkg.core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    d = [T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)]
+    ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq, pt, gq, gt, obj, want_adds=False)
+    order = torch.randperm(B, generator=torch.Generator().manual_seed(n)).to(torch.int32).to(cuda_dev)
+    for o in (None, order):
+        add, _, hit, valid, _ = table.evaluate(*d, want_adds=False, order=o)
+        assert same_bits(add.cpu().numpy(), ref[0])
+        assert np.array_equal(hit.cpu().numpy(), ref[2]) and np.array_equal(valid.cpu().numpy(), ref[3])
+    assert valid.cpu().numpy().sum() == B - 3
+
+
 def test_packed_sqrt_equals_sqrt_rn_on_every_float(pkg, cuda_dev):
     """sqrt2_rn (kernel (a)'s packed square root) against sqrt.rn.f32 over all 2^32 bit patterns."""
     assert pkg.core.selftest_sqrt2(cuda_dev.index) == 0
