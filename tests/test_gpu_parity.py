@@ -541,6 +541,18 @@ def test_pinhole_forward_backward(pkg, cuda_dev):
     assert same_bits(out.cpu().numpy(), g["out_shared"])
 
 
+def test_pinhole_shared_k_vector_kernel_equals_the_row_kernel(pkg, cuda_dev, oracle):
+    """Shared [3,3] K and B >= 1024: four rows per thread with 16-byte accesses; B % 4 = 1, 2, 3 tails."""
+    r = np.random.RandomState(9)
+    K = pkg.DEFAULT_K.astype(np.float32)
+    for B in (1024, 4097, 10002, 65539):
+        z = (r.rand(B, 1) * 1.2 + 0.3).astype(np.float32)
+        uv = (r.rand(B, 2) * np.array([640, 480])).astype(np.float32)
+        got = pkg.pinhole_translation(T(z, cuda_dev), T(uv, cuda_dev), T(K, cuda_dev)).cpu().numpy()
+        ref, _ = oracle.pinhole(z, uv, K)
+        assert same_bits(got, ref), B
+
+
 def test_depth_backproject(pkg, cuda_dev, W, oracle):
     g = load_golden("depth_backproject")
     depth, uv, K = W.config4(256, int(g["seed"]))
