@@ -176,8 +176,22 @@ def cpu_rate(W, n_poses, threads=None):
     return n_poses / dt, threads, dt
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is meant to use every host
+    core it can (only rank 0 runs it), so the intra-op pool is sized to the CPUs this process may run on."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    if torch.get_num_threads() != n:
+        torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
 def real_reference():
     """(root, criterion of the UNMODIFIED reference on the CPU with the config-2 meshes) or (None, why)."""
+    use_all_host_threads()
     try:
         from oracle import torch_eager as E
         root = E.find_reference()
@@ -674,7 +688,7 @@ def run_b200(args):
                 line["secondary"] = secondary_rooflines(pkg, dev, peaks.get("hbm_gbs"), peak)
             except Exception as e:  # never lose the headline line over the side measurements
                 line["secondary"] = {"error": repr(e)}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:        # the CPU leg belongs to the N = 1 line only
             line["cpu_baseline"] = cpu_baseline_record(args, W, r)
         emit(line)
     if world > 1:
