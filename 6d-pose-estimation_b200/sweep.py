@@ -183,7 +183,7 @@ def variant_translation(variant: str, block: dict, K):
     return depth_backproject(block["depth"], block["uv"], block["kc"], clamp_hi=7.0)
 
 
-def evaluate_sweep(points: dict, diameters: dict, device, n_per_block: int, variants=VARIANTS, chunk: int = 262144,
+def evaluate_sweep(points: dict, diameters: dict, device, n_per_block: int, variants=VARIANTS, chunk: int = 1 << 20,
                    seed: int = 5000, rank: int = 0, world: int = 1, group=None, K=None, check_n: int = 0,
                    rot_sigma: float = 0.05, trans_sigma: float = 0.005, evaluator: "PoseEvaluator | None" = None):
     """compare_all_models-style sweep (reference scripts/visualization/compare_all_models.py:65-104 at the

@@ -14,7 +14,8 @@ dev = torch.device("cuda", 0)
 per = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
 sizes = [5, 11, 64, 200, 500, 777, 1000, 1500, 2048, 3000]
 bits = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
-tot = {"poses": 0, "add_mismatch": 0, "adds_mismatch": 0, "hit_mismatch": 0, "valid_mismatch": 0, "hits": 0}
+tot = {"poses": 0, "add_mismatch": 0, "adds_mismatch": 0, "hit_mismatch": 0, "valid_mismatch": 0, "hits": 0,
+       "add_only_mismatch": 0, "add_only_single_mesh_mismatch": 0, "add_only_poses": 0}
 t0 = time.time()
 for si, n in enumerate(sizes):
     B = max(256, int(per * min(1.0, (500.0 / n) ** 2)))       # keep the CPU side bounded for large meshes
@@ -38,6 +39,15 @@ for si, n in enumerate(sizes):
     tot["hit_mismatch"] += int((got["hit"] != ref[2]).sum())
     tot["valid_mismatch"] += int((got["valid"] != ref[3]).sum())
     tot["hits"] += int(ref[2].sum())
+    # kernel (a) on the same poses: two-mesh table (negotiated staging) and a single-mesh table (barrier-free form)
+    dv = [torch.from_numpy(x).to(dev) for x in (pq, pt, gq, gt, obj)]
+    a2 = crit._mesh_table(dev).evaluate(*dv, want_adds=False)[0].cpu().numpy()
+    tot["add_only_mismatch"] += int((bits(a2) != bits(ref[0])).sum())
+    one = pkg.core.MeshTable({0: pts[0]}, {0: dia[0]}, pkg.SYMMETRIC_OBJECT_IDS, dev)
+    a1 = one.evaluate(*dv, want_adds=False)[0].cpu().numpy()
+    sel = obj == 0
+    tot["add_only_single_mesh_mismatch"] += int((bits(a1[sel]) != bits(ref[0][sel])).sum()) + int((a1[~sel] != 0).sum())
+    tot["add_only_poses"] += 2 * B
 tot["mesh_sizes"] = sizes
 tot["seconds"] = round(time.time() - t0, 1)
 print(json.dumps(tot))
