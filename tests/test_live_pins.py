@@ -235,3 +235,62 @@ def test_fused_crop_kernel_equals_cv2_run_on_this_box(pkg, cuda_dev, W):
         finally:
             if has_ipp:
                 cv2.ipp.setUseIPP(True)
+
+
+@pytest.mark.gpu
+def test_eval_metrics_dict_equals_the_unmodified_reference_on_this_box(pkg, cuda_dev, eager, W):
+    """Drop-in check against the reference itself (baseline/_ref, installed by build()): the dict
+    ``ADDLoss.eval_metrics`` returns -- float64 means over the batch in mm / per cent -- is EQUAL, key by
+    key, to what the unmodified reference computes on this box's CPU for the same batch, the way
+    compare_all_models.py calls it (batches of 16), incl. ids without a mesh and an all-unknown batch."""
+    import tempfile
+    root = eager.find_reference()
+    if root is None:
+        pytest.skip("no reference checkout on this machine")
+    pts = {0: W.sphere_mesh(500, 0.102, 21), 4: W.sphere_mesh(300, 0.2, 22), 9: W.box_mesh(500, (0.1, 0.12, 0.05), 23),
+           10: W.box_mesh(420, (0.04, 0.17, 0.04), 24)}
+    dia = {0: 0.102, 4: 0.2, 9: 0.1646, 10: 0.1759}
+    ref_crit = eager.reference_criterion(root, pts, dia)
+    crit = pkg.ADDLoss(tempfile.mkdtemp(), cuda_dev)
+    for k, v in pts.items():
+        crit.points[k] = torch.from_numpy(v).to(cuda_dev)
+    crit.diameters.update(dia)
+    B = 16
+    ids = np.array([0, 4, 9, 10, 7], np.int64)              # 7 has no mesh
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    for batch in range(6):
+        pq, pt, gq, gt = _poses(W, B, 300 + batch)
+        obj = ids[np.random.RandomState(batch).randint(0, 5, B)] if batch < 5 else np.full(B, 7, np.int64)
+        want = ref_crit.eval_metrics(Tc(pq), Tc(pt), Tc(gq), Tc(gt), Tc(obj))
+        got = crit.eval_metrics(*(Tc(x).to(cuda_dev) for x in (pq, pt, gq, gt, obj)))
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k] == want[k] and type(got[k]) is type(want[k]), (batch, k, got[k], want[k])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["geodesic", "l1"])
+def test_pose_loss_equals_the_unmodified_reference_on_this_box(pkg, cuda_dev, eager, W, mode):
+    """PoseLoss forward + backward against the reference's own class (baseline/_ref/models/pose_loss.py)
+    run on this box's CPU: loss within 1e-5, gradients within 1e-5 of the row maximum."""
+    import importlib.util, os, sys
+    root = eager.find_reference()
+    if root is None:
+        pytest.skip("no reference checkout on this machine")
+    spec = importlib.util.spec_from_file_location("_p6d_reference_pose_loss", os.path.join(root, "models", "pose_loss.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    c = W.config3(32, 17)
+    Tc = lambda x: torch.from_numpy(np.ascontiguousarray(x))
+    ref_rot, ref_tr = Tc(c["rot_raw"]).requires_grad_(True), Tc(c["gt_trans"] + 0.013).requires_grad_(True)
+    ref = mod.PoseLoss(1.0, 10.0, mode)(ref_rot, ref_tr, Tc(c["gt_rot"]), Tc(c["gt_trans"]))
+    ref.backward()
+    rot, tr = Tc(c["rot_raw"]).to(cuda_dev).requires_grad_(True), Tc(c["gt_trans"] + 0.013).to(cuda_dev).requires_grad_(True)
+    got = pkg.PoseLoss(1.0, 10.0, mode)(rot, tr, Tc(c["gt_rot"]).to(cuda_dev), Tc(c["gt_trans"]).to(cuda_dev))
+    got.backward()
+    assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    g_ref = ref_rot.grad.numpy()
+    sc = np.maximum(np.abs(g_ref).max(1, keepdims=True), 1e-30)
+    assert np.all(np.abs(rot.grad.cpu().numpy() - g_ref) <= 1e-5 * sc)
+    assert np.allclose(tr.grad.cpu().numpy(), ref_tr.grad.numpy(), rtol=1e-6, atol=0)
