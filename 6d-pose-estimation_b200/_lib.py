@@ -208,28 +208,46 @@ class MeshTable:
             pass
 
     # -- device-buffer evaluation ---------------------------------------------------
-    def evaluate(self, pq, pt, gq, gt, obj, want_adds=True, order=None, acc=None):
-        """Launch the evaluation kernels on the current stream.  All tensors must already
-        be contiguous CUDA tensors on this table's device.  Returns (add, adds, hit, valid, packed)
-        device tensors (adds is None when want_adds is False); `packed` is the one buffer behind
-        them: add f32 | adds f32 | hit u8 | valid u8 | borderline u8."""
+    def evaluate_packed(self, pq, pt, gq, gt, obj, want_adds=True, order=None, acc=None):
+        """Launch the evaluation kernels on the current stream and return the ONE buffer behind the
+        per-pose outputs: add f32 [B] | adds f32 [B] | hit u8 [B] | valid u8 [B] | borderline u8 [B]
+        (adds is left unwritten when want_adds is False).  All inputs must already be contiguous CUDA
+        tensors on this table's device.  No views are created: at the reference's batch sizes every
+        torch op is 2-3 us of a ~100 us call."""
         B = obj.shape[0]
-        dev = self.device
-        # one allocation -> one D2H copy later
-        out = torch.empty(11 * B + 16, dtype=torch.uint8, device=dev)
-        add = out[: 4 * B].view(torch.float32)
-        adds = out[4 * B: 8 * B].view(torch.float32)
-        hit = out[8 * B: 9 * B]
-        valid = out[9 * B: 10 * B]
-        border = out[10 * B: 11 * B]
+        out = torch.empty(11 * B + 16, dtype=torch.uint8, device=self.device)
+        base = out.data_ptr()
         acc_struct = None
         if acc is not None:
             acc_struct = Accumulators(*(ptr(a) for a in acc))
-        check(lib().p6d_add_eval(self.handle, ptr(pq), ptr(pt), ptr(gq), ptr(gt), ptr(obj), ptr(order), B,
-                                 ptr(add), ptr(adds) if want_adds else None, ptr(hit), ptr(valid), ptr(border),
-                                 C.byref(acc_struct) if acc_struct is not None else None,
-                                 stream_ptr(dev)))
-        return add, (adds if want_adds else None), hit, valid, out
+        check(lib().p6d_add_eval(self.handle, pq.data_ptr(), pt.data_ptr(), gq.data_ptr(), gt.data_ptr(), obj.data_ptr(),
+                                 ptr(order), B, base, (base + 4 * B) if want_adds else None, base + 8 * B, base + 9 * B,
+                                 base + 10 * B, C.byref(acc_struct) if acc_struct is not None else None,
+                                 stream_ptr(self.device)))
+        return out
+
+    def evaluate(self, pq, pt, gq, gt, obj, want_adds=True, order=None, acc=None):
+        """evaluate_packed + views: returns (add, adds, hit, valid, packed) device tensors (adds is
+        None when want_adds is False)."""
+        B = obj.shape[0]
+        out = self.evaluate_packed(pq, pt, gq, gt, obj, want_adds, order, acc)
+        add = out[: 4 * B].view(torch.float32)
+        adds = out[4 * B: 8 * B].view(torch.float32)
+        return add, (adds if want_adds else None), out[8 * B: 9 * B], out[9 * B: 10 * B], out
+
+    def packed_to_host(self, packed):
+        """The packed per-pose buffer as a NumPy array: one async copy into a cached pinned buffer and one
+        stream synchronisation (the only synchronisation of an eval_metrics call).  The array is a view of
+        the cached buffer: consume it before the next call."""
+        n = packed.numel()
+        buf = getattr(self, "_pinned", None)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 4096), dtype=torch.uint8).pin_memory()
+            self._pinned = buf
+        host = buf[:n]
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
 
     def forward_loss(self, pq, pt, gq, gt, obj):
         """ADDLoss.forward value: one launch, no host synchronisation.  Returns (loss [1] f32,

@@ -164,8 +164,9 @@ class ADDLoss(nn.Module):
         """{'add_mean' [mm], 'add_s_mean' [mm], 'add_01d_acc' [%]} over the poses whose
         object has a mesh; int 0 entries when there is none (reference :156-201)."""
         per_pose = self.eval_poses(pred_r, pred_t, gt_r, gt_t, obj_ids)
-        keep = per_pose["valid"].astype(bool)
-        if not keep.any():
+        keep = per_pose["valid"].view(np.bool_)
+        n_keep = int(np.count_nonzero(keep))
+        if n_keep == 0:
             return {"add_mean": 0, "add_s_mean": 0, "add_01d_acc": 0}
         hit = per_pose["hit"]
         if self.borderline_resolver is not None and per_pose["borderline"].any():
@@ -175,11 +176,16 @@ class ADDLoss(nn.Module):
             if idx.size:
                 hit = hit.copy()
                 hit[idx] = np.asarray(self.borderline_resolver(idx, pred_r, pred_t, gt_r, gt_t, obj_ids), np.uint8)
-        # the reference averages Python floats on the host: float64 np.mean
+        add, add_s = per_pose["add"], per_pose["add_s"]
+        if n_keep != keep.shape[0]:
+            add, add_s, hit = add[keep], add_s[keep], hit[keep]
+        # the reference averages lists of Python floats on the host: np.mean over a float64 ARRAY
+        # (np.mean(x32, dtype=float64) casts in 8192-element buffers and sums in another pairwise order:
+        # it differs in the last bit from 65,536 elements on)
         return {
-            "add_mean": np.mean(per_pose["add"][keep].astype(np.float64)) * 1000,
-            "add_s_mean": np.mean(per_pose["add_s"][keep].astype(np.float64)) * 1000,
-            "add_01d_acc": np.mean(hit[keep].astype(np.float64)) * 100,
+            "add_mean": np.mean(add.astype(np.float64)) * 1000,
+            "add_s_mean": np.mean(add_s.astype(np.float64)) * 1000,
+            "add_01d_acc": np.mean(hit.astype(np.float64)) * 100,
         }
 
     @torch.no_grad()
@@ -194,8 +200,7 @@ class ADDLoss(nn.Module):
             zb = np.zeros(B, np.uint8)
             return {"add": z, "add_s": z.copy(), "hit": zb, "valid": zb.copy(), "borderline": zb.copy()}
         table = self._mesh_table(dev)
-        _, _, _, _, packed = table.evaluate(pq, pt, gq, gt, obj, True, order)
-        host = packed.cpu().numpy()       # the only synchronisation of the call
+        host = table.packed_to_host(table.evaluate_packed(pq, pt, gq, gt, obj, True, order)).copy()
         return {"add": host[:4 * B].view(np.float32), "add_s": host[4 * B:8 * B].view(np.float32),
                 "hit": host[8 * B:9 * B], "valid": host[9 * B:10 * B], "borderline": host[10 * B:11 * B]}
 
