@@ -413,13 +413,14 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
 
     del d8, uv8, o8, K, z, uv, o
     m = 1 << 20
-    pts = {0: W.sphere_mesh(1000, 0.102, 100)}
-    table = core.MeshTable(pts, {0: 0.102}, pkg.SYMMETRIC_OBJECT_IDS, dev)
     obj = torch.zeros(m, dtype=torch.int64, device=dev)
     qa, ta = torch.nn.functional.normalize(rnd(m, 4), dim=1), rnd(m, 3)
     qb, tb = torch.nn.functional.normalize(qa + 0.05 * rnd(m, 4), dim=1), ta + 0.005 * rnd(m, 3)
-    t = timed(lambda: table.evaluate(qb, tb, qa, ta, obj, want_adds=False), 5)
-    fp32_row("add_pose_kernel (a), ADD only, N=1000", m, 46 * 1000, t, hbm_gbs=m * 73 / t / 1e9)
+    for npts in (1000, 500):            # 500 points = the reference loader's own mesh size
+        pts = {0: W.sphere_mesh(npts, 0.102, 100)}
+        table = core.MeshTable(pts, {0: 0.102}, pkg.SYMMETRIC_OBJECT_IDS, dev)
+        t = timed(lambda: table.evaluate_packed(qb, tb, qa, ta, obj, want_adds=False), 5)
+        fp32_row(f"add_pose_kernel (a), ADD only, N={npts}", m, 46 * npts, t, hbm_gbs=m * 73 / t / 1e9)
     for npts, Bn in ((500, 1 << 20), (1000, 1 << 18)):
         pts = {9: W.box_mesh(npts, (0.1, 0.12, 0.05), 200 + npts)}
         tb_ = core.MeshTable(pts, {9: 0.1646}, pkg.SYMMETRIC_OBJECT_IDS, dev)
