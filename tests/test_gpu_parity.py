@@ -207,8 +207,51 @@ def test_add_only_kernel_single_mesh_table(pkg, cuda_dev, W, oracle, n):
     assert valid.cpu().numpy().sum() == B - 3
 
 
+@pytest.mark.parametrize("single", [False, True])
+def test_add_only_kernel_large_launch_batches_of_poses_per_warp(pkg, cuda_dev, W, oracle, single):
+    """Kernel (a) hands a warp BATCHES of up to 32 poses once a launch is large enough (lane l prepares pose l,
+    the matrices go through shared memory, batches are claimed through an atomic counter).  A 1.3 M-pose launch
+    (32 poses per batch) must give the bits of the same poses in 4,096-pose launches (one pose per warp, the
+    form the other tests pin to the oracle) -- unsorted (every batch mixes objects: one staging pass per
+    object and round), sorted, with ids that have no mesh, exact zeros (the scalar re-evaluation), NaN -- and
+    a random subset is compared with the oracle directly."""
+    if single:
+        pts = {3: W.sphere_mesh(500, 0.12, 901)}
+        ids = np.array([3, 3, 3, 3, 3, 3, 3, 7], np.int64)
+    else:
+        pts = {1: W.sphere_mesh(500, 0.1, 911), 2: W.sphere_mesh(1000, 0.1, 912), 4: W.sphere_mesh(37, 0.1, 913),
+               5: W.sphere_mesh(2048, 0.1, 914), 6: W.sphere_mesh(131, 0.1, 915), 9: W.sphere_mesh(8, 0.1, 916),
+               10: W.sphere_mesh(1, 0.1, 917), 12: W.sphere_mesh(416, 0.1, 918)}
+        ids = np.array([1, 2, 4, 5, 6, 9, 10, 12, 3, 99, -1, 1, 1, 2], np.int64)
+    dia = {k: 0.1 for k in pts}
+    B = 1_300_000
+    pq, pt, gq, gt = W.random_poses(B, 61, rot_sigma=np.geomspace(0.005, 0.3, B))
+    r = np.random.RandomState(62)
+    obj = ids[r.randint(0, len(ids), B)]
+    same = r.choice(B, 300, replace=False)
+    pq[same] = gq[same]; pt[same] = gt[same]          # every distance exactly 0: the pose is re-evaluated by the scalar path
+    pt[r.choice(B, 50, replace=False), 1] = np.nan
+    table = pkg.core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    d = [T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)]
+    small = [torch.cat([table.evaluate(*(x[lo:lo + 4096] for x in d), want_adds=False)[k] for lo in range(0, B, 4096)])
+             for k in (0, 2, 3)]
+    order = torch.argsort(d[4], stable=True).to(torch.int32)
+    for o in (None, order):
+        add, _, hit, valid, _ = table.evaluate(*d, want_adds=False, order=o)
+        assert torch.equal(add.view(torch.int32), small[0].view(torch.int32))
+        assert torch.equal(hit, small[1]) and torch.equal(valid, small[2])
+    sel = np.concatenate([r.choice(B, 6000, replace=False), same[:40]])
+    ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq[sel], pt[sel], gq[sel], gt[sel], obj[sel], want_adds=False,
+                          n_threads=oracle.max_threads())
+    sel_t = torch.from_numpy(sel).to(cuda_dev)
+    assert same_bits(add[sel_t].cpu().numpy(), ref[0])
+    assert np.array_equal(hit[sel_t].cpu().numpy(), ref[2]) and np.array_equal(valid[sel_t].cpu().numpy(), ref[3])
+    assert int(valid.sum()) == int(np.isin(obj, list(pts)).sum())
+
+
 def test_packed_sqrt_equals_sqrt_rn_on_every_float(pkg, cuda_dev):
-    """sqrt2_rn (kernel (a)'s packed square root) against sqrt.rn.f32 over all 2^32 bit patterns."""
+    """sqrt2_rn and the unchecked four-way form + its range test (kernel (a)'s packed square roots) against
+    sqrt.rn.f32 over all 2^32 bit patterns."""
     assert pkg.core.selftest_sqrt2(cuda_dev.index) == 0
 
 
