@@ -8,12 +8,12 @@ reference's own imports (``from models.add_loss import ADDLoss`` ...).
 from . import _lib as core  # noqa: F401  (registers p6d_b200_core)
 from .models.add_loss import ADDLoss, SYMMETRIC_OBJECT_IDS  # noqa: F401
 from .models.pose_loss import PoseLoss  # noqa: F401
-from .utils.camera import (DEFAULT_K, depth_backproject, depth_crop_backproject, get_gt_and_K,  # noqa: F401
-                           pinhole_translation)
+from .utils.camera import (DEFAULT_K, depth_backproject, depth_crop_backproject, detection_backproject,  # noqa: F401
+                           get_gt_and_K, pinhole_translation)
 from . import workloads  # noqa: F401
 from . import sweep  # noqa: F401
 from .sweep import PoseEvaluator, evaluate_sweep, reference_batch_means, shard_range  # noqa: F401
 
 __all__ = ["ADDLoss", "PoseLoss", "SYMMETRIC_OBJECT_IDS", "DEFAULT_K", "get_gt_and_K",
-           "pinhole_translation", "depth_backproject", "depth_crop_backproject", "core", "workloads", "sweep", "PoseEvaluator",
+           "pinhole_translation", "depth_backproject", "depth_crop_backproject", "detection_backproject", "core", "workloads", "sweep", "PoseEvaluator",
            "evaluate_sweep", "reference_batch_means", "shard_range"]

@@ -25,7 +25,7 @@ SO_PATH = os.path.join(CSRC, "libp6d.so")
 
 P6D_OK, P6D_EINVAL, P6D_ECUDA, P6D_ENOMEM, P6D_ETOOBIG = 0, -1, -2, -3, -4
 
-P6D_VERSION = 3
+P6D_VERSION = 4
 
 EXPORTS = (
     "p6d_version", "p6d_last_error", "p6d_device_info", "p6d_mesh_table_create",
@@ -34,7 +34,7 @@ EXPORTS = (
     "p6d_add_forward_workspace_bytes", "p6d_add_forward", "p6d_add_backward",
     "p6d_quat_to_mat", "p6d_pose_loss_workspace_bytes", "p6d_pose_loss_fwd_bwd",
     "p6d_pose_loss_pinhole_fwd_bwd", "p6d_pinhole_fwd", "p6d_pinhole_bwd", "p6d_depth_backproject",
-    "p6d_depth_crop_backproject", "p6d_project_points", "p6d_synth_poses", "p6d_sweep_run",
+    "p6d_depth_crop_backproject", "p6d_detection_backproject", "p6d_project_points", "p6d_synth_poses", "p6d_sweep_run",
     "p6d_adds_tf32_eval", "p6d_fp32_microbench",
 )
 
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     L.p6d_depth_backproject.argtypes = [vp, i32, i32, vp, vp, i32, i64, f32, vp, i32, vp]
     L.p6d_fp32_microbench.argtypes = [i32, i32, i32, C.POINTER(f64), C.POINTER(f64)]
     L.p6d_depth_crop_backproject.argtypes = [vp, i32, i32, vp, i64, vp, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.p6d_detection_backproject.argtypes = [vp, i32, i32, vp, i64, vp, i32, vp, vp, vp, vp, i32, vp]
     L.p6d_project_points.argtypes = [vp, i32, vp, i32, vp, vp, i64, vp, i32, vp]
     L.p6d_add_backward.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp, vp, f32, vp, vp, vp]
     missing = [n for n in EXPORTS if not hasattr(L, n)]

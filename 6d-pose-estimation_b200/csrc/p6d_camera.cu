@@ -228,6 +228,76 @@ __global__ void __launch_bounds__(CAM_T) depth_crop_backproject_kernel(
 }
 
 // ---------------------------------------------------------------------------------
+// N1, inference form: the per-detection crop code of scripts/inference/inference_rgbd_geometric.py:109-170
+// fused with (d2).  Differs from the dataset form above in three places, each of which moves a rounding:
+// detector boxes are integer (x1, y1, x2, y2); the crop is cast to float32 BEFORE cv2.resize, so the
+// resized depth is the un-rounded float32 lerp (IPP's ippiResizeLinear_32f: the same float64 coordinate /
+// float32 weight / one fma per lerp as its 16-bit form); centre and K_crop are computed in float64 (Python
+// floats, the float64 DEFAULT_K) and only the results are stored as float32.
+__global__ void __launch_bounds__(CAM_T) detection_backproject_kernel(
+    const unsigned short* __restrict__ depth, int H, int W, const int* __restrict__ boxes, int64_t B,
+    const double* __restrict__ K, int img, float* __restrict__ xyz, float* __restrict__ center_out,
+    float* __restrict__ kcrop_out, float* __restrict__ zm_out) {
+    const double fx = K[0], cx = K[2], fy = K[4], cy = K[5];
+    for (int64_t b = (int64_t)blockIdx.x * CAM_T + threadIdx.x; b < B; b += (int64_t)gridDim.x * CAM_T) {
+        const int4 bb = *reinterpret_cast<const int4*>(boxes + 4 * b);
+        // Python scalars: float64 and int() truncation toward zero
+        const double c_x = ((double)bb.x + (double)bb.z) / 2.0, c_y = ((double)bb.y + (double)bb.w) / 2.0;
+        const long long w = (long long)bb.z - bb.x, h = (long long)bb.w - bb.y;
+        const double size = (double)(w > h ? w : h) * 1.2;
+        const long long crop_x1 = (long long)__dsub_rn(c_x, size / 2.0), crop_y1 = (long long)__dsub_rn(c_y, size / 2.0);
+        const long long cs = (long long)size;
+        if (cs < 1) {  // degenerate box: the reference would fail in cv2.resize; emit the fallback depth
+            xyz[3 * b] = 0.0f; xyz[3 * b + 1] = 0.0f; xyz[3 * b + 2] = 0.5f;
+            if (center_out) { center_out[2 * b] = 0.0f; center_out[2 * b + 1] = 0.0f; }
+            if (kcrop_out) for (int k = 0; k < 9; ++k) kcrop_out[9 * b + k] = 0.0f;
+            if (zm_out) zm_out[b] = 0.0f;
+            continue;
+        }
+        const long long pad_l = crop_x1 < 0 ? -crop_x1 : 0, pad_t = crop_y1 < 0 ? -crop_y1 : 0;
+        const long long adj_x1 = crop_x1 + pad_l, adj_y1 = crop_y1 + pad_t;
+        const double scale = (double)img / (double)cs;
+        const float hi = (float)(img - 1);
+        // float64 products, stored as float32 (np.array(..., dtype=np.float32)), then np.clip in float32
+        float u = (float)__dmul_rn(__dsub_rn(__dadd_rn(c_x, (double)pad_l), (double)adj_x1), scale);
+        float v = (float)__dmul_rn(__dsub_rn(__dadd_rn(c_y, (double)pad_t), (double)adj_y1), scale);
+        u = u < 0.0f ? 0.0f : (u > hi ? hi : u);
+        v = v < 0.0f ? 0.0f : (v > hi ? hi : v);
+        const float fxc = (float)__dmul_rn(fx, scale), fyc = (float)__dmul_rn(fy, scale);
+        const float cxc = (float)__dmul_rn(__dsub_rn(__dadd_rn(cx, (double)pad_l), (double)crop_x1), scale);
+        const float cyc = (float)__dmul_rn(__dsub_rn(__dadd_rn(cy, (double)pad_t), (double)crop_y1), scale);
+        int ui = (int)u, vi = (int)v;              // .long(): truncation, then clamp
+        ui = ui < 0 ? 0 : (ui > img - 1 ? img - 1 : ui);
+        vi = vi < 0 ? 0 : (vi > img - 1 ? img - 1 : vi);
+        auto texel = [&](int yy, int xx) -> float {
+            const long long fy_ = adj_y1 + yy - pad_t, fx_ = adj_x1 + xx - pad_l;
+            if (fy_ < 0 || fy_ >= H || fx_ < 0 || fx_ >= W) return 0.0f;   // cv2.copyMakeBorder(..., value=0)
+            return (float)__ldg(depth + fy_ * W + fx_);
+        };
+        int sx0, sx1, sy0, sy1;
+        float wx, wy;
+        resize_axis_ipp(ui, cs, img, sx0, sx1, wx);
+        resize_axis_ipp(vi, cs, img, sy0, sy1, wy);
+        const float t00 = texel(sy0, sx0), t01 = texel(sy0, sx1), t10 = texel(sy1, sx0), t11 = texel(sy1, sx1);
+        const float h0 = __fmaf_rn(__fsub_rn(t01, t00), wx, t00);
+        const float h1 = __fmaf_rn(__fsub_rn(t11, t10), wx, t10);
+        const float val = __fmaf_rn(__fsub_rn(h1, h0), wy, h0);
+        const float zm = __fdiv_rn(val, 1000.0f);  // crop_depth_resized / 1000.0 (float32 array / Python float)
+        float z = (zm > 0.01f) ? zm : 0.5f;
+        z = z < 0.1f ? 0.1f : (z > 2.0f ? 2.0f : z);
+        xyz[3 * b + 0] = __fdiv_rn(__fmul_rn(__fsub_rn(u, cxc), z), fxc);
+        xyz[3 * b + 1] = __fdiv_rn(__fmul_rn(__fsub_rn(v, cyc), z), fyc);
+        xyz[3 * b + 2] = z;
+        if (center_out) { center_out[2 * b] = u; center_out[2 * b + 1] = v; }
+        if (kcrop_out) {
+            float* k = kcrop_out + 9 * b;
+            k[0] = fxc; k[1] = 0.0f; k[2] = cxc; k[3] = 0.0f; k[4] = fyc; k[5] = cyc; k[6] = 0.0f; k[7] = 0.0f; k[8] = 1.0f;
+        }
+        if (zm_out) zm_out[b] = zm;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // N4: utils/visualization.project_points for B poses (float64 like the reference's NumPy).
 __global__ void __launch_bounds__(CAM_T) project_points_kernel(const double* __restrict__ pts, int N,
                                                                const double* __restrict__ rot, int is_quat,
@@ -369,6 +439,29 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
     if (rc) return rc;
     depth_crop_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
         depth, H, W, boxes, B, K, img_size, bilinear, xyz, center, kcrop, z_mm);
+    P6D_CUDA(cudaGetLastError());
+    return P6D_OK;
+}
+
+int p6d_detection_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes_xyxy, int64_t B,
+                              const double* K, int img_size, float* xyz, float* center, float* kcrop, float* z_m,
+                              int device, void* stream) {
+    if (B < 0 || H < 1 || W < 1 || img_size < 1 || (B > 0 && (!depth || !boxes_xyxy || !K || !xyz))) {
+        set_error("p6d_detection_backproject: bad arguments");
+        return P6D_EINVAL;
+    }
+    if (reinterpret_cast<uintptr_t>(boxes_xyxy) & 15u) {
+        set_error("p6d_detection_backproject: boxes must be 16-byte aligned (int4 rows)");
+        return P6D_EINVAL;
+    }
+    if (B == 0) return P6D_OK;
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    unsigned grid;
+    int rc = grid_for(B, device, &grid);
+    if (rc) return rc;
+    detection_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
+        depth, H, W, boxes_xyxy, B, K, img_size, xyz, center, kcrop, z_m);
     P6D_CUDA(cudaGetLastError());
     return P6D_OK;
 }

@@ -169,3 +169,42 @@ def depth_crop_backproject(depth_frame, boxes, camera_matrix, img_size=224, retu
     if return_aux:
         return xyz, center, kcrop, zmm.view(torch.uint16)
     return xyz
+
+
+def detection_backproject(depth_frame, boxes_xyxy, camera_matrix=None, img_size=224, return_aux=False):
+    """XYZ for every integer (x1, y1, x2, y2) detector box of one uint16 depth frame [H,W] (millimetres)
+    without materialising any crop: the per-detection crop code of the reference's inference script
+    (scripts/inference/inference_rgbd_geometric.py:109-170: pad, square crop of 1.2 x max(w, h),
+    ``cv2.resize`` of the crop cast to float32, centre and K_crop in float64) fused with the depth
+    back-projection of models/pose_net_rgbd_geometric.py:56-85.  `camera_matrix` is the frame's [3,3] K
+    in float64 (default: DEFAULT_K, as in the script).  With return_aux also returns (centre [B,2],
+    K_crop [B,3,3], z_m [B] float32 = ``depth_meters`` under the centre)."""
+    core = _core()
+    if not isinstance(depth_frame, torch.Tensor):
+        depth_frame = torch.from_numpy(np.ascontiguousarray(depth_frame, dtype=np.uint16))
+    if not isinstance(boxes_xyxy, torch.Tensor):
+        boxes_xyxy = torch.from_numpy(np.ascontiguousarray(boxes_xyxy, dtype=np.int32))
+    K = DEFAULT_K if camera_matrix is None else camera_matrix
+    if not isinstance(K, torch.Tensor):
+        K = torch.from_numpy(np.ascontiguousarray(K, dtype=np.float64))
+    dev = core.require_cuda(depth_frame.device if depth_frame.is_cuda else boxes_xyxy.device if boxes_xyxy.is_cuda
+                            else K.device)
+    if depth_frame.dim() != 2 or depth_frame.dtype not in (torch.uint16, torch.int16):
+        raise ValueError("depth_frame must be a [H,W] uint16 tensor (millimetres)")
+    if K.numel() != 9:
+        raise ValueError("camera_matrix must be the frame's [3,3] intrinsics")
+    d = depth_frame.to(dev).contiguous()
+    bx = boxes_xyxy.to(dev, torch.int32).reshape(-1, 4).contiguous()
+    K = K.to(dev, torch.float64).contiguous()
+    B = bx.shape[0]
+    H, W = d.shape
+    xyz = torch.empty(B, 3, dtype=torch.float32, device=dev)
+    center = torch.empty(B, 2, dtype=torch.float32, device=dev) if return_aux else None
+    kcrop = torch.empty(B, 3, 3, dtype=torch.float32, device=dev) if return_aux else None
+    zm = torch.empty(B, dtype=torch.float32, device=dev) if return_aux else None
+    core.check(core.lib().p6d_detection_backproject(core.ptr(d), H, W, core.ptr(bx), B, core.ptr(K), int(img_size),
+                                                    core.ptr(xyz), core.ptr(center), core.ptr(kcrop), core.ptr(zm),
+                                                    dev.index, core.stream_ptr(dev)))
+    if return_aux:
+        return xyz, center, kcrop, zm
+    return xyz

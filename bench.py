@@ -401,6 +401,14 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
                                                               224, 0, xyzb.data_ptr(), None, None, None, dev.index, st)))
     hbm_row("depth_crop_backproject (N1), 2^20 boxes of one frame (frame stays in L2: 16 B box + 12 B out per row)",
             big.shape[0], 28, t)
+    # N1, inference form: integer xyxy detector boxes, float32 resize, float64 centre / K_crop
+    xyxy = bx.clone()
+    xyxy[:, 2:] += xyxy[:, :2]
+    K64 = torch.tensor(pkg.DEFAULT_K, dtype=torch.float64, device=dev).contiguous()
+    t = timed(lambda: core.check(L.p6d_detection_backproject(dfr.data_ptr(), 480, 640, xyxy.data_ptr(), 256, K64.data_ptr(), 224,
+                                                             xyz.data_ptr(), None, None, None, dev.index, st)), 20)
+    res.append({"kernel": "detection_backproject (N1, inference-script form): 480x640 uint16 frame, 256 xyxy boxes",
+                "bound": "latency", "boxes": 256, "us": round(t * 1e6, 2), "boxes_per_s": 256 / t})
 
     # FP32-issue-bound rows: (a) ADD only, (b) ADD-S at the reference's mesh sizes
     def fp32_row(kernel, poses, flop_per_pose, t, **extra):

@@ -37,7 +37,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define P6D_VERSION 3
+#define P6D_VERSION 4
 
 #define P6D_OK 0
 #define P6D_EINVAL (-1)   /* bad argument */
@@ -236,6 +236,18 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
 int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes, int64_t B,
                                const float* K, int img_size, int bilinear, float* xyz, float* center,
                                float* kcrop, uint16_t* z_mm, int device, void* stream);
+
+/* The same fusion for the INFERENCE script's per-detection crop code
+ * (scripts/inference/inference_rgbd_geometric.py:109-170, then models/pose_net_rgbd_geometric.py:56-85):
+ * B integer detector boxes (x1,y1,x2,y2) of ONE uint16 depth frame [H,W] in millimetres, K [3,3] in
+ * FLOAT64 (the script passes utils.camera.DEFAULT_K, a float64 array, and computes centre and K_crop in
+ * float64 before storing them as float32).  The crop is cast to float32 before cv2.resize there, so the
+ * depth under the centre is the un-rounded float32 lerp of the pip wheel's default path
+ * (ippiResizeLinear_32f), reproduced bit for bit; OpenCV's own C++ float path is not offered.
+ *   xyz [B,3]; optional center [B,2], kcrop [B,9], z_m [B] (depth_meters under the centre, float32). */
+int p6d_detection_backproject(const uint16_t* depth, int H, int W, const int32_t* boxes_xyxy, int64_t B,
+                              const double* K, int img_size, float* xyz, float* center, float* kcrop,
+                              float* z_m, int device, void* stream);
 
 /* 3-D -> 2-D projection of N model points for B poses:
  * utils/visualization.project_points (utils/visualization.py:8-32) in float64 --

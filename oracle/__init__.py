@@ -328,6 +328,81 @@ def resize_linear_u16(img, size=224, bilinear="cv2"):
     return np.clip(np.rint(out), 0, 65535).astype(np.uint16)
 
 
+def resize_linear_f32(img, size=224):
+    """cv2.resize(img_f32, (size, size)) with INTER_LINEAR for a square float32 image, as the OpenCV pip wheel
+    computes it by default (IPP, ippiResizeLinear_32f) -- the call of the reference's inference script
+    (scripts/inference/inference_rgbd_geometric.py:140): the arithmetic of resize_linear_u16(bilinear="cv2")
+    without the final rounding.  Identified by probing (0 mismatching bit patterns for crops of 48..576 pixels,
+    tests/test_live_pins.py re-checks it against the local cv2).  OpenCV's own C++ path for float32
+    (cv2.ipp.setUseIPP(False)) is NOT restated: it differs from  a*(1-w) + b*w  in a few pixels when up-sampling."""
+    f, d64 = np.float32, np.float64
+    I = np.asarray(img, f)
+    cs = I.shape[0]
+    assert I.shape == (cs, cs)
+    d = np.arange(size)
+    c = (d + 0.5) * (cs / float(size)) - 0.5
+    s = np.floor(c).astype(np.int64)
+    w = np.where(s < 0, 0.0, c - s).astype(f)
+    s0, s1 = np.clip(s, 0, cs - 1), np.clip(s + 1, 0, cs - 1)
+    lerp = lambda a, b, ww: ((b.astype(d64) - a.astype(d64)).astype(f).astype(d64) * ww.astype(d64) + a.astype(d64)).astype(f)
+    hor = lerp(I[:, s0], I[:, s1], np.broadcast_to(w, (cs, size)))
+    return lerp(hor[s0], hor[s1], np.broadcast_to(w[:, None], (size, size)))
+
+
+def detection_depth_backproject(depth_u16, boxes_xyxy, K, img_size=224):
+    """N1, inference form (NumPy, per box): the per-detection crop code of the reference's inference script
+    (scripts/inference/inference_rgbd_geometric.py:109-170) -- integer (x1, y1, x2, y2) detector boxes, square
+    crop of 1.2 x max(w, h) cut from the zero-padded uint16 frame, cv2.resize of the crop CAST TO FLOAT32
+    (resize_linear_f32), centre and K_crop computed in float64 (Python floats, float64 DEFAULT_K) and only then
+    stored as float32 -- followed by the depth back-projection of models/pose_net_rgbd_geometric.py:56-85 at the
+    one pixel the network reads.  Differs from the dataset form (crop_depth_backproject) in the box format, in
+    where float32 rounding happens and in the un-rounded float32 depth."""
+    f = np.float32
+    depth = np.asarray(depth_u16)
+    H, Wd = depth.shape
+    K = np.asarray(K, np.float64)
+    B = len(boxes_xyxy)
+    center = np.zeros((B, 2), f); Kc = np.zeros((B, 3, 3), f); z_m = np.zeros(B, f); xyz = np.zeros((B, 3), f)
+    for b in range(B):
+        x1, y1, x2, y2 = (int(v) for v in boxes_xyxy[b])
+        c_x, c_y = (x1 + x2) / 2, (y1 + y2) / 2
+        w, h = x2 - x1, y2 - y1
+        size = max(w, h) * 1.2
+        crop_x1, crop_y1 = int(c_x - size / 2), int(c_y - size / 2)
+        cs = int(size)
+        pad_l, pad_t = max(0, -crop_x1), max(0, -crop_y1)
+        adj_x1, adj_y1 = crop_x1 + pad_l, crop_y1 + pad_t
+        scale = img_size / cs                                              # float64
+        cr = np.clip(np.array([(c_x + pad_l - adj_x1) * scale, (c_y + pad_t - adj_y1) * scale], dtype=f), 0, img_size - 1)
+        center[b] = cr
+        fx_, fy_, cx_, cy_ = K[0, 0], K[1, 1], K[0, 2], K[1, 2]
+        Kc[b] = np.array([[fx_ * scale, 0, (cx_ + pad_l - crop_x1) * scale],
+                          [0, fy_ * scale, (cy_ + pad_t - crop_y1) * scale], [0, 0, 1]], dtype=f)
+        u, v = cr[0], cr[1]
+        ui, vi = min(max(int(u), 0), img_size - 1), min(max(int(v), 0), img_size - 1)
+
+        def tx(yy, xx):
+            fy, fx = adj_y1 + yy - pad_t, adj_x1 + xx - pad_l
+            return f(depth[fy, fx]) if (0 <= fy < H and 0 <= fx < Wd) else f(0)
+
+        def axis(d):
+            c = (d + 0.5) * (cs / float(img_size)) - 0.5
+            s = int(np.floor(c))
+            return min(max(s, 0), cs - 1), min(max(s + 1, 0), cs - 1), (f(0) if s < 0 else f(c - s))
+
+        sx0, sx1, wx = axis(ui)
+        sy0, sy1, wy = axis(vi)
+        h0 = fma32(f(tx(sy0, sx1) - tx(sy0, sx0)), wx, tx(sy0, sx0))
+        h1 = fma32(f(tx(sy1, sx1) - tx(sy1, sx0)), wx, tx(sy1, sx0))
+        val = fma32(f(h1 - h0), wy, h0)
+        z = f(val / f(1000.0))
+        z_m[b] = z
+        z = z if z > f(0.01) else f(0.5)
+        z = min(max(z, f(0.1)), f(2.0))
+        xyz[b] = (f(f(f(u - Kc[b, 0, 2]) * z) / Kc[b, 0, 0]), f(f(f(v - Kc[b, 1, 2]) * z) / Kc[b, 1, 1]), z)
+    return {"center": center, "Kcrop": Kc, "z_m": z_m, "xyz": xyz}
+
+
 def crop_depth_backproject(depth_u16, boxes, K, img_size=224, bilinear="cv2"):
     """N1 restatement (NumPy, per box): the crop geometry of LineMODDatasetRGBD.__getitem__
     (data/dataset_rgbd.py:104-179, no augmentation), cv2.resize's INTER_LINEAR for uint16

@@ -389,6 +389,45 @@ def gen_crop_ipp():
     save("crop_backproject_ipp", **out)
 
 
+def gen_crop_xyxy():
+    """N1, inference form: the per-detection crop code of the reference's inference script
+    (scripts/inference/inference_rgbd_geometric.py, the body of `for box in results[0].boxes:` up to the model
+    call) EXECUTED FROM THE REFERENCE'S OWN SOURCE FILE -- the script is not importable (YOLO, weights,
+    matplotlib), so its lines are read from /root/reference at generation time, dedented and exec'ed per box with
+    a stand-in detection object; nothing of it is stored here -- followed by the reference's
+    PoseNetRGBDGeometric._compute_pinhole_translation on what those lines produced."""
+    import textwrap, types
+    import cv2
+    src = open(os.path.join(REF, "scripts", "inference", "inference_rgbd_geometric.py")).read().splitlines()
+    lo = next(i for i, l in enumerate(src) if "map(int, box.xyxy[0])" in l)
+    hi = next(i for i, l in enumerate(src) if "# Pose inference" in l)
+    body = compile(textwrap.dedent("\n".join(src[lo:hi])), "inference_rgbd_geometric.py[per-detection]", "exec")
+    depth, boxes = W.config4_frame(41, 256)
+    xyxy = np.stack([boxes[:, 0], boxes[:, 1], boxes[:, 0] + boxes[:, 2], boxes[:, 1] + boxes[:, 3]], 1).astype(np.int32)
+    xyxy[:6] = [(300, 200, 674, 300),      # crop 448 = 2 x 224, crosses the right border
+                (200, 150, 387, 250),      # crop 224: identity
+                (10, 10, 30, 40),          # crop 36: x6.2 up-sampling
+                (-40, -30, 120, 90),       # negative corner: padding on the left and top
+                (500, 380, 700, 520),      # crosses the bottom-right corner
+                (100, 100, 101, 103)]      # crop of 3 pixels
+    h_img, w_img = depth.shape
+    net = PoseNetRGBDGeometric.__new__(PoseNetRGBDGeometric)
+    centers, Ks, zs, xyzs = [], [], [], []
+    for b in xyxy:
+        ns = dict(box=types.SimpleNamespace(xyxy=[torch.tensor([float(v) for v in b])], cls=[0], conf=[0.9]),
+                  CLASS_ID_TO_OBJ_NAME={0: "01"}, rgb_img=np.zeros((h_img, w_img, 3), np.uint8), depth_img=depth,
+                  h_img=h_img, w_img=w_img, img_size=224, K=DEFAULT_K.copy(), cv2=cv2, np=np, torch=torch,
+                  transform=lambda a: torch.zeros(3, 224, 224), device="cpu")
+        exec(body, ns)
+        xyz = PoseNetRGBDGeometric._compute_pinhole_translation(net, ns["input_depth_raw"], ns["bbox_center"], ns["cam_matrix"])
+        c = ns["bbox_center"][0].numpy()
+        u, v = (int(np.clip(np.clip(c[k], 0, 223).astype(np.int64), 0, 223)) for k in (0, 1))
+        centers.append(c); Ks.append(ns["cam_matrix"][0].numpy()); xyzs.append(xyz[0].numpy())
+        zs.append(ns["input_depth_raw"][0, v, u].numpy())
+    save("crop_backproject_xyxy", seed=np.int64(41), boxes_xyxy=xyxy, K=DEFAULT_K.astype(np.float64), center=np.stack(centers),
+         Kcrop=np.stack(Ks), z_m=np.array(zs, np.float32), xyz=np.stack(xyzs), cv2_version=np.array(cv2.__version__))
+
+
 def gen_projection():
     """N4: utils/mesh_utils.load_mesh_corners (PLY -> 1/99 percentile box corners) and
     utils/visualization.project_points (scipy quaternion -> R, pinhole projection, int
@@ -420,7 +459,7 @@ def gen_projection():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    gen_quat(); gen_eval(); gen_forward(); gen_forward_more(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_crop_ipp(); gen_projection()
+    gen_quat(); gen_eval(); gen_forward(); gen_forward_more(); gen_pose_loss(); gen_pinhole(); gen_depth(); gen_loader(); gen_crop(); gen_crop_ipp(); gen_crop_xyxy(); gen_projection()
     with open(os.path.join(OUT, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by oracle/gen_golden.py from {REF}\n"
                 f"torch {torch.__version__} cpu_capability {torch.backends.cpu.get_cpu_capability()} "

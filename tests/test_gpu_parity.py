@@ -691,6 +691,30 @@ def test_depth_crop_backproject_fused(pkg, cuda_dev, W, oracle):
     assert pkg.depth_crop_backproject(depth2, boxes2[:0], K).shape == (0, 3)
 
 
+def test_detection_backproject_inference_form(pkg, cuda_dev, W, oracle):
+    """N1, inference form on the GPU (integer xyxy detector boxes, float32 resize, float64 centre / K_crop):
+    bit-equal to the values the reference's own inference-script lines + model method produced, and to the
+    oracle on another frame size with boxes partly outside the frame."""
+    g = load_golden("crop_backproject_xyxy")
+    depth, _ = W.config4_frame(int(g["seed"]), 256)
+    xyz, center, kcrop, zm = pkg.detection_backproject(torch.from_numpy(depth).to(cuda_dev), g["boxes_xyxy"], g["K"],
+                                                       return_aux=True)
+    assert same_bits(center.cpu().numpy(), g["center"]) and same_bits(kcrop.cpu().numpy(), g["Kcrop"])
+    assert same_bits(zm.cpu().numpy(), g["z_m"]) and same_bits(xyz.cpu().numpy(), g["xyz"])
+    # default K = DEFAULT_K (float64), as in the script
+    assert same_bits(pkg.detection_backproject(torch.from_numpy(depth).to(cuda_dev), g["boxes_xyxy"]).cpu().numpy(), g["xyz"])
+    depth2, b2 = W.config4_frame(43, 3000, hw=(360, 500))
+    xyxy = np.stack([b2[:, 0], b2[:, 1], b2[:, 0] + b2[:, 2], b2[:, 1] + b2[:, 3]], 1).astype(np.int32)
+    xyxy[:8, [0, 2]] -= 60; xyxy[8:16, [1, 3]] += 200; xyxy[16] = (5, 5, 5, 5)      # the last one: empty box -> fallback
+    r = oracle.detection_depth_backproject(depth2, xyxy[:16], g["K"])
+    got = pkg.detection_backproject(torch.from_numpy(depth2).to(cuda_dev), xyxy, g["K"], return_aux=True)
+    assert same_bits(got[0][:16].cpu().numpy(), r["xyz"]) and same_bits(got[3][:16].cpu().numpy(), r["z_m"])
+    assert got[0][16].tolist() == [0.0, 0.0, 0.5]
+    r = oracle.detection_depth_backproject(depth2, xyxy[17:600], g["K"])
+    assert same_bits(got[0][17:600].cpu().numpy(), r["xyz"]) and same_bits(got[1][17:600].cpu().numpy(), r["center"])
+    assert pkg.detection_backproject(torch.from_numpy(depth2).to(cuda_dev), xyxy[:0]).shape == (0, 3)
+
+
 def test_two_tables_of_different_size_interleaved(pkg, cuda_dev, W, oracle):
     """The ADD-S kernel's shared-memory attribute is per device, not per table: a small and a
     large table used alternately must both keep launching (and keep their results)."""

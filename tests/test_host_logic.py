@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(pkg):
     missing = [s for s in sorted(declared) if not hasattr(L, s)]
     assert not missing, missing
     assert set(pkg.core.EXPORTS) == declared
-    assert pkg.core.lib().p6d_version() == pkg.core.P6D_VERSION == 3
+    assert pkg.core.lib().p6d_version() == pkg.core.P6D_VERSION == 4
     # the product library carries none of the development hooks
     assert not hasattr(L, "p6d_adds_timeline")
     blob = open(pkg.core.SO_PATH, "rb").read()

@@ -199,6 +199,52 @@ def test_borderline_flags_and_the_resolver_hook(pkg, cuda_dev, eager, W):
     assert m["add_01d_acc"] == np.mean(ref[2].astype(np.float64)) * 100
 
 
+def test_float32_resize_restatement_equals_the_local_cv2(oracle):
+    """The inference script resizes the crop as float32 (scripts/inference/inference_rgbd_geometric.py:140): the
+    local cv2's default INTER_LINEAR on CV_32F against oracle.resize_linear_f32, whole 224x224 outputs, bit for bit
+    (skipped when the local OpenCV has no IPP: its own C++ float path is not restated)."""
+    cv2 = pytest.importorskip("cv2")
+    if not (hasattr(cv2, "ipp") and cv2.ipp.useIPP()):
+        pytest.skip("OpenCV without IPP")
+    r = np.random.RandomState(8)
+    for cs in (3, 36, 97, 150, 223, 224, 225, 301, 448, 449, 576):
+        img = r.randint(400, 1500, (cs, cs)).astype(np.uint16)
+        img[r.rand(cs, cs) < 0.1] = 0
+        out = cv2.resize(img.astype(np.float32), (224, 224))
+        assert np.array_equal(out.view(np.uint32), oracle.resize_linear_f32(img, 224).view(np.uint32)), cs
+
+
+@pytest.mark.gpu
+def test_detection_kernel_equals_cv2_run_on_this_box(pkg, cuda_dev, W):
+    """N1, inference form, against cv2 itself ON THE GPU BOX: for detector boxes whose crop lies inside the frame,
+    the float32 depth the kernel returns equals the pixel of cv2.resize(crop.astype(float32)) / 1000 the
+    reference's script would hand to the network."""
+    cv2 = pytest.importorskip("cv2")
+    if not (hasattr(cv2, "ipp") and cv2.ipp.useIPP()):
+        pytest.skip("OpenCV without IPP")
+    depth, _ = W.config4_frame(48, 8)
+    r = np.random.RandomState(49)
+    n = 400
+    w = r.randint(30, 300, n); h = r.randint(30, 300, n)
+    x = (r.rand(n) * (640 - 1.2 * np.maximum(w, h)) + 0.1 * np.maximum(w, h)).astype(np.int64)
+    y = (r.rand(n) * (480 - 1.2 * np.maximum(w, h)) + 0.1 * np.maximum(w, h)).astype(np.int64)
+    xyxy = np.stack([x, y, x + w, y + h], 1).astype(np.int32)
+    _, center, _, zm = pkg.detection_backproject(torch.from_numpy(depth).to(cuda_dev), xyxy, return_aux=True)
+    center, zm = center.cpu().numpy(), zm.cpu().numpy()
+    checked = 0
+    for b in range(n):
+        x1, y1, x2, y2 = (int(v) for v in xyxy[b])
+        size = max(x2 - x1, y2 - y1) * 1.2
+        cx1, cy1, cs = int((x1 + x2) / 2 - size / 2), int((y1 + y2) / 2 - size / 2), int(size)
+        if cx1 < 0 or cy1 < 0 or cx1 + cs > 640 or cy1 + cs > 480:
+            continue                           # padded boxes are covered by the golden fixture
+        crop = cv2.resize(depth[cy1:cy1 + cs, cx1:cx1 + cs].astype(np.float32), (224, 224)) / 1000.0
+        u, v = int(min(max(center[b, 0], 0), 223)), int(min(max(center[b, 1], 0), 223))
+        assert np.float32(crop[v, u]).view(np.uint32) == zm[b].view(np.uint32), (b, xyxy[b])
+        checked += 1
+    assert checked > 100
+
+
 @pytest.mark.gpu
 def test_fused_crop_kernel_equals_cv2_run_on_this_box(pkg, cuda_dev, W):
     """N1 against cv2 itself ON THE GPU BOX: for boxes inside the frame, the z_mm the kernel returns

@@ -142,6 +142,19 @@ def test_crop_pipeline_restatement_matches_reference_dataset(oracle, W):
         assert np.array_equal(r["z_mm"], g[f"{tag}_z_mm"]) and same_bits(r["xyz"], g[f"{tag}_xyz"])
 
 
+def test_detection_crop_restatement_matches_the_reference_inference_script(oracle, W):
+    """N1, inference form: integer xyxy boxes, float32 cv2.resize of the crop, float64 centre / K_crop -- against
+    values produced by the per-detection lines of the reference's own inference script, executed from its source
+    file (oracle/gen_golden.py gen_crop_xyxy), then its PoseNetRGBDGeometric method.  Boxes include the exact-2x
+    crop, the identity crop, x6 up-sampling, negative corners, border crossings and a 3-pixel crop."""
+    g = load_golden("crop_backproject_xyxy")
+    depth, _ = W.config4_frame(int(g["seed"]), 256)
+    r = oracle.detection_depth_backproject(depth, g["boxes_xyxy"], g["K"])
+    assert same_bits(r["center"], g["center"]) and same_bits(r["Kcrop"], g["Kcrop"])
+    assert same_bits(r["z_m"], g["z_m"]) and same_bits(r["xyz"], g["xyz"])
+    assert len(np.unique(g["z_m"])) > 100 and (g["z_m"] != np.round(g["z_m"] * 1000) / 1000).any()   # un-rounded depths occur
+
+
 def test_crop_pipeline_on_pixels_where_ipp_and_generic_bilinear_disagree(oracle, W):
     """The fixture that separates the two arithmetics: 65 of its 256 boxes read a pixel whose value
     differs by 1 mm between cv2's default and its generic path (found by search, values produced by
