@@ -620,6 +620,16 @@ int launch_eval(const p6d_mesh_table* t, const EvalArgs& args, bool want_adds, c
         if (rc == P6D_OK && launches) ++*launches;
         return rc;
     }
+    if (force_variant < 0 && !args.sample) {
+        // opt-in (p6d_mesh_table_set_pruning): the exact-pruned kernel where the table qualifies
+        bool used = false;
+        const int rc = launch_eval_pruned(t, args, st, false, &used);
+        if (rc != P6D_OK) return rc;
+        if (used) {
+            if (launches) ++*launches;
+            return P6D_OK;
+        }
+    }
     int vi = force_variant;
     if (vi < 0) {
         const int rc = pick_variant(t, args.sample != nullptr, st, &vi);
@@ -788,6 +798,10 @@ int p6d_adds_max_points(int device, int* max_points) {
     return P6D_OK;
 }
 
+// block structure of the opt-in pruned ADD-S kernel (p6d_adds_pruned.cu)
+void p6d_internal_build_pruned(const p6d_mesh_table* t, const float* xyz, const int32_t* offsets);
+void p6d_internal_release_pruned(const p6d_mesh_table* t);
+
 int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_t* counts,
                           const double* diameters, const uint8_t* symmetric, int n_slots, int device,
                           p6d_mesh_table** out) {
@@ -862,6 +876,7 @@ int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_
         return fail(e, "cudaMemcpy(pair)");
     if ((e = cudaMemcpy(t->d_slots, t->h_slots, n_slots * sizeof(SlotInfo), cudaMemcpyHostToDevice)) != cudaSuccess)
         return fail(e, "cudaMemcpy(slots)");
+    p6d_internal_build_pruned(t, xyz, offsets);
     *out = t;
     return P6D_OK;
 }
@@ -869,6 +884,7 @@ int p6d_mesh_table_create(const float* xyz, const int32_t* offsets, const int32_
 int p6d_mesh_table_destroy(p6d_mesh_table* t) {
     if (!t) return P6D_OK;
     DeviceGuard guard(t->device);
+    p6d_internal_release_pruned(t);
     if (t->stream) cudaStreamDestroy(t->stream);
     if (t->d_stage) cudaFree(t->d_stage);
     if (t->h_pinned) cudaFreeHost(t->h_pinned);

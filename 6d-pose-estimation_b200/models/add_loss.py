@@ -75,9 +75,13 @@ class ADDLoss(nn.Module):
         self.trans_weight = trans_weight
         self._table = None
         self._table_key = None
+        self._table_pruning = False
         # optional callable(indices, pred_r, pred_t, gt_r, gt_t, obj_ids) -> 0/1 per index, consulted by
         # eval_metrics for decisions flagged `borderline`; None (default): the kernel's decision stands
         self.borderline_resolver = None
+        # opt-in: exact block pruning in the ADD-S kernel (same bits; pays for meshes of >= 768 points, the
+        # all-pairs kernel is kept below that) -- not part of the reference surface, default off
+        self.exact_pruning = False
         self._load_models(model_dir)
 
     # ------------------------------------------------------------------ loading
@@ -139,6 +143,10 @@ class ADDLoss(nn.Module):
                 self._table.close()
             self._table = _core().MeshTable(self.points, self.diameters, SYMMETRIC_OBJECT_IDS, device)
             self._table_key = key
+            self._table_pruning = False
+        if bool(self.exact_pruning) != self._table_pruning:
+            self._table.set_pruning(bool(self.exact_pruning))
+            self._table_pruning = bool(self.exact_pruning)
         return self._table
 
     def _prepare(self, pred_r, pred_t, gt_r, gt_t, obj_ids, sort=True):

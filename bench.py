@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--no-microbench", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary kernels")
     ap.add_argument("--no-sweep", action="store_true", help="skip the config-5 sweep record")
+    ap.add_argument("--no-pruned", action="store_true", help="skip the record of the opt-in exact-pruned ADD-S kernel")
     ap.add_argument("--sweep-per-block", type=int, default=1_000_000, help="hypotheses per (object, variant) block")
     ap.add_argument("--sweep-points", default="500,2048", help="mesh sizes of the sweep record")
     ap.add_argument("--sweep-check", type=int, default=256, help="poses per block checked against the oracle")
@@ -475,7 +476,7 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
 
 
 # ------------------------------------------------------------------------- config 5
-def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barrier):
+def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barrier, exact_pruning=False):
     """BASELINE config 5 for one mesh size: 13 objects x 4 variants x n_per_block hypotheses, the hypothesis
     axis of every block sliced over the ranks (strong scaling), one native call per rank
     (p6d_sweep_run) + one all-reduce of the accumulators.  The first poses of every block of every rank's
@@ -486,7 +487,7 @@ def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barr
     W = pkg.workloads
     variants = pkg.sweep.VARIANTS
     pts, dia = W.sweep_meshes(n_points)
-    ev = pkg.PoseEvaluator(pts, dia, dev, n_rows=len(variants))
+    ev = pkg.PoseEvaluator(pts, dia, dev, n_rows=len(variants), exact_pruning=exact_pruning)
     # warm-up through the same code path (also runs the one-time self-check of a re-laid kernel)
     pkg.evaluate_sweep(pts, dia, dev, 4096 * world, seed=SWEEP_SEED, rank=rank, world=world, evaluator=ev)
     ev.acc.zero_()
@@ -523,6 +524,7 @@ def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barr
                         f"{n_points}-point meshes, ADD + ADD-S + ADD-0.1d for every pose; hypotheses generated on the device "
                         "(p6d_synth_poses), translations of the geometric variants by kernels (d1) / (d2)",
             "n_points": n_points, "hypotheses": total, "scaling": "strong", "n_gpus": world,
+            "adds_kernel": "exact-pruned (opt-in)" if exact_pruning else "all-pairs",
             "seconds": wall_s, "device_seconds": dev_s, "poses_per_s": total / wall_s,
             "tflops": total * (8 * n_points * n_points + 46 * n_points) / wall_s / 1e12,
             "launches_per_rank": launches,
@@ -644,6 +646,43 @@ def run_b200(args):
         for npts in [int(x) for x in args.sweep_points.split(",") if x]:
             sweeps[f"n{npts}"] = sweep_record(pkg, dev, rank, world, npts, args.sweep_per_block, args.sweep_check, barrier)
 
+    # ---------------- opt-in exact-pruned ADD-S kernel (b'): the SAME outputs from less work.  Reported on its own:
+    # `value`, `roofline` and `sweep` above are the all-pairs kernel the north-star names.
+    pruned = None
+    if not args.no_pruned and B == POSES_PER_GPU:
+        ptable = core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, dev).set_pruning(True)
+        ref_out = table.evaluate_packed(*d_in, want_adds=True, order=order)
+        pr_out = ptable.evaluate_packed(*d_in, want_adds=True, order=order)
+        equal = bool(torch.equal(ref_out[:10 * B], pr_out[:10 * B]))     # add, adds, hit, valid: every byte
+        for _ in range(3):
+            ptable.evaluate_packed(*d_in, want_adds=True, order=order)
+        barrier()
+        pe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)
+            pe[k][0].record()
+            ptable.evaluate_packed(*d_in, want_adds=True, order=order)
+            pe[k][1].record()
+        barrier()
+        pms = torch.tensor([sum(a.elapsed_time(b) for a, b in pe)], dtype=torch.float64, device=dev)
+        eq = torch.tensor([1 if equal else 0], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(pms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+        pruned = {"what": "opt-in exact block pruning in the ADD-S kernel (p6d_mesh_table_set_pruning / ADDLoss.exact_pruning): "
+                          "gt blocks that provably hold no nearest neighbour are skipped; every output byte equals the "
+                          "all-pairs kernel's. Not a roofline number: it does less work",
+                  "value": world * B * args.steps / (float(pms.item()) * 1e-3), "unit": UNIT, "workload": "the config-2 step above",
+                  "ms_per_step": float(pms.item()) / args.steps, "outputs_equal_all_pairs": bool(eq.item()),
+                  "speedup_vs_all_pairs": (world * B * args.steps / (float(pms.item()) * 1e-3)) / value}
+        if sweeps.get("n2048") is not None:
+            ps = sweep_record(pkg, dev, rank, world, 2048, args.sweep_per_block, args.sweep_check, barrier, exact_pruning=True)
+            pruned["sweep_n2048"] = {k: ps[k] for k in ("seconds", "device_seconds", "poses_per_s", "hits_per_variant",
+                                                         "hits_table_sha256", "oracle_check", "adds_kernel")}
+            pruned["sweep_n2048"]["hits_table_equals_all_pairs"] = ps["hits_table_sha256"] == sweeps["n2048"]["hits_table_sha256"]
+            pruned["sweep_n2048"]["speedup_vs_all_pairs"] = sweeps["n2048"]["seconds"] / ps["seconds"]
+        del ptable
+
     if rank == 0:
         kernel_ms = float(np.mean(step_ms))            # rank 0's kernel; at N = 1 the step is the kernel
         achieved = B * FLOP_PER_POSE / (kernel_ms * 1e-3) / 1e12
@@ -692,6 +731,8 @@ def run_b200(args):
                 "add_01d_acc": 100.0 * hits / valid}
         if sweeps:
             line["sweep"] = sweeps
+        if pruned:
+            line["pruned"] = pruned
         if not args.no_secondary and B == POSES_PER_GPU:
             try:
                 line["secondary"] = secondary_rooflines(pkg, dev, peaks.get("hbm_gbs"), peak)

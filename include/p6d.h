@@ -125,6 +125,23 @@ int p6d_add_eval(const p6d_mesh_table* table, const float* pq, const float* pt, 
                  float* adds, uint8_t* hit, uint8_t* valid, uint8_t* borderline,
                  const p6d_accumulators* acc, void* stream);
 
+/* OPT-IN: the same outputs, bit for bit, from a kernel that skips gt points which provably cannot be a
+ * nearest neighbour (exact block pruning: the mesh is cut into spatially compact 32-point blocks at table
+ * creation; per pose a block pair is skipped when the distance of its bounding spheres exceeds the current
+ * minima, with margins far above float32 error; anything that is not a number is evaluated).  Not the
+ * all-pairs kernel the headline numbers are measured on, and never reported as a roofline fraction.
+ *   p6d_add_eval_pruned          always this kernel; adds must not be NULL; a table whose largest mesh exceeds
+ *                                ~4,700 points (shared memory) or 65,534 points answers P6D_ETOOBIG
+ *   p6d_mesh_table_set_pruning   per-table switch (default off): p6d_add_eval, p6d_add_eval_host and p6d_sweep_run
+ *                                then take this kernel where it pays -- largest mesh of the table >= 768 points
+ *                                and within the shared-memory limit -- and the all-pairs kernel otherwise
+ *                                (the loss form p6d_add_forward always takes the all-pairs kernel). */
+int p6d_mesh_table_set_pruning(p6d_mesh_table* table, int enable);
+int p6d_add_eval_pruned(const p6d_mesh_table* table, const float* pq, const float* pt, const float* gq,
+                        const float* gt, const int64_t* obj, const int32_t* order, int64_t B, float* add,
+                        float* adds, uint8_t* hit, uint8_t* valid, uint8_t* borderline,
+                        const p6d_accumulators* acc, void* stream);
+
 /* Same computation with HOST buffers: stages inputs to the device, runs the kernels,
  * copies results back and synchronises (the end-to-end path of bench.py).  acc_* are
  * host arrays [n_slots] that receive (not accumulate) the per-object totals; nullable.

@@ -715,6 +715,84 @@ def test_detection_backproject_inference_form(pkg, cuda_dev, W, oracle):
     assert pkg.detection_backproject(torch.from_numpy(depth2).to(cuda_dev), xyxy[:0]).shape == (0, 3)
 
 
+def _edge_poses(W, B, seed, sigma):
+    pq, pt, gq, gt = W.random_poses(B, seed, rot_sigma=sigma)
+    pq[3] = gq[3]; pt[3] = gt[3]                      # identical poses: every distance 0
+    pt[4, 0] = np.nan                                 # NaN propagates through every minimum
+    pq[5] = np.nan
+    pt[6, 2] = np.inf
+    pq[7] *= 3.0                                      # non-unit quaternion: R is not a rotation (spheres must not assume it)
+    pq[8] = 0.0                                       # zero quaternion: R = I scaled to ... whatever _quat_to_mat gives
+    gq[9] *= 1e-3
+    return pq, pt, gq, gt
+
+
+@pytest.mark.parametrize("sizes", [(2048, 1000), (3000, 33, 64), (500, 131, 1), (777, 1024, 1500, 2)])
+def test_exact_pruned_adds_kernel_equals_all_pairs(pkg, cuda_dev, W, oracle, sizes):
+    """The opt-in pruned ADD-S kernel (b') must return every byte the all-pairs kernel returns -- ADD, ADD-S,
+    decisions, valid flags, borderline flags -- for good and bad predictions, mixed objects in any order, ids
+    without a mesh, NaN / inf / zero / non-unit poses; a subset is compared with the oracle directly."""
+    pts = {k + 1: (W.sphere_mesh(n, 0.1, 400 + n) if k % 2 == 0 else W.box_mesh(n, (0.1, 0.12, 0.05), 500 + n))
+           for k, n in enumerate(sizes)}
+    dia = {k: 0.1 for k in pts}
+    table = pkg.core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    B = 6000
+    for sigma in (0.01, 0.1, 1.0):
+        pq, pt, gq, gt = _edge_poses(W, B, 70 + len(sizes), np.full(B, sigma))
+        obj = np.array(list(pts) + [0, 99, -3], np.int64)[np.random.RandomState(71).randint(0, len(pts) + 3, B)]
+        d = [T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)]
+        order = torch.argsort(d[4], stable=True).to(torch.int32)
+        for o in (None, order):
+            full = table.evaluate(*d, order=o)[4]
+            prun = table.evaluate(*d, order=o, prune=True)[4]
+            assert torch.equal(full[:11 * B], prun[:11 * B]), (sizes, sigma)
+        sel = np.random.RandomState(72).choice(B, 64, replace=False)
+        ref = oracle.add_eval(oracle.MeshTable(pts, dia), pq[sel], pt[sel], gq[sel], gt[sel], obj[sel],
+                              n_threads=oracle.max_threads())
+        adds = prun[4 * B:8 * B].view(torch.float32).cpu().numpy()
+        assert same_bits(adds[sel], ref[1])
+
+
+def test_exact_pruning_switch_degenerate_meshes_and_limits(pkg, cuda_dev, W, oracle):
+    """The per-table switch (ADDLoss.exact_pruning / MeshTable.set_pruning) changes no result; meshes whose
+    blocks degenerate (all points equal, collinear points, a NaN vertex) stay exact; a mesh beyond the pruned
+    kernel's shared-memory limit is refused by the explicit entry and silently takes the all-pairs kernel
+    under the switch."""
+    r = np.random.RandomState(80)
+    line = np.zeros((900, 3), np.float32); line[:, 0] = np.linspace(-0.05, 0.05, 900)
+    same = np.full((800, 3), 0.01, np.float32)
+    bad = W.sphere_mesh(1000, 0.1, 81).copy(); bad[17, 1] = np.nan
+    pts = {1: line, 2: same, 3: bad, 4: W.sphere_mesh(1200, 0.1, 82)}
+    dia = {k: 0.1 for k in pts}
+    B = 2000
+    pq, pt, gq, gt = _edge_poses(W, B, 83, np.geomspace(0.005, 0.5, B))
+    obj = r.randint(1, 5, B).astype(np.int64)
+    d = [T(x, cuda_dev) for x in (pq, pt, gq, gt, obj)]
+    table = pkg.core.MeshTable(pts, dia, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    full = table.evaluate(*d)[4]
+    assert torch.equal(full[:11 * B], table.evaluate(*d, prune=True)[4][:11 * B])
+    table.set_pruning(True)
+    assert torch.equal(full[:11 * B], table.evaluate(*d)[4][:11 * B])          # through p6d_add_eval, switch on
+    host = table.evaluate_host(pq, pt, gq, gt, obj)                              # and through the host entry
+    assert same_bits(host["adds"], full[4 * B:8 * B].view(torch.float32).cpu().numpy())
+    # ADDLoss surface: the aggregate dict does not change with the switch
+    crit = make_crit(pkg, {k: v for k, v in pts.items() if k != 3}, dia, cuda_dev)
+    keep = obj != 3
+    args = [T(x[keep], cuda_dev) for x in (pq, pt, gq, gt, obj)]
+    m0 = crit.eval_metrics(*args)
+    crit.exact_pruning = True
+    m1 = crit.eval_metrics(*args)
+    assert {k: repr(v) for k, v in m0.items()} == {k: repr(v) for k, v in m1.items()}
+    # beyond the pruned kernel's limit
+    big = pkg.core.MeshTable({0: W.sphere_mesh(6000, 0.1, 84)}, {0: 0.1}, pkg.SYMMETRIC_OBJECT_IDS, cuda_dev)
+    e = [T(x[:8], cuda_dev) for x in (pq, pt, gq, gt)] + [torch.zeros(8, dtype=torch.long, device=cuda_dev)]
+    with pytest.raises(pkg.core.P6DError, match="at most"):
+        big.evaluate(*e, prune=True)
+    ref = big.evaluate(*e)[4]
+    big.set_pruning(True)
+    assert torch.equal(ref[:88], big.evaluate(*e)[4][:88])
+
+
 def test_two_tables_of_different_size_interleaved(pkg, cuda_dev, W, oracle):
     """The ADD-S kernel's shared-memory attribute is per device, not per table: a small and a
     large table used alternately must both keep launching (and keep their results)."""

@@ -15,7 +15,7 @@ for step in "$@"; do
     search1024) SEARCH_CHECKPOINT=$OUT/${TAG}_plan1024.json timeout $(( ${SEARCH_S:-240} + 240 )) python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi256ELi4ELi4ELi0ELi0EE 1 1000 262144 ${SEARCH_S:-240} 6d-pose-estimation_b200/csrc/sched_plan_n1024.json 3,0 > $OUT/${TAG}_search1024.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search1024.log; tail -4 $OUT/${TAG}_search1024.log | cut -c1-600 ;;
     search512)  SEARCH_CHECKPOINT=$OUT/${TAG}_plan512.json timeout $(( ${SEARCH_S:-240} + 240 )) python tools/sched_search.py tools/sched_exp/libp6d_unsched.so adds_cta_kernelILi128ELi4ELi8ELi0ELi0EE 0 500 1048576 ${SEARCH_S:-240} 6d-pose-estimation_b200/csrc/sched_plan_n512.json 8,0 > $OUT/${TAG}_search512.log 2>&1; echo "rc=$?" >> $OUT/${TAG}_search512.log; tail -4 $OUT/${TAG}_search512.log | cut -c1-600 ;;
     ncu)    # launch list + full capture of the headline kernel + the secondary kernels (only after bench exited 0)
-            BARGS="--no-sweep --no-secondary --no-cpu-baseline --no-microbench"
+            BARGS="--no-sweep --no-pruned --no-secondary --no-cpu-baseline --no-microbench"
             timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 $BARGS > $OUT/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?"
             timeout 400 ncu --set full --clock-control none --import-source on -k regex:adds_cta --launch-skip 3 -c 1 -f -o $OUT/adds_${TAG} python bench.py --steps 2 --warmup 3 $BARGS > $OUT/${TAG}_ncu_adds.log 2>&1; echo "adds capture rc=$?"
             timeout 600 ncu --set full --clock-control none --import-source on -k regex:'add_pose|pose_loss|pinhole|depth|add_backward|quat|tf32|synth|adds_cta' -f -o $OUT/secondary_${TAG} python tools/profile_small.py > $OUT/${TAG}_ncu_secondary.log 2>&1; echo "secondary capture rc=$?"; tail -2 $OUT/${TAG}_ncu_secondary.log ;;
