@@ -8,15 +8,17 @@
 // ADD-S = mean_i min_j |pred_i - gt_j| (reference models/add_loss.py:185-190).  Only the minimum of every row has
 // to be exact; any pair that is provably not below the current minimum may be skipped.  Both clouds are the SAME
 // mesh under two rigid (or at least linear) maps, so the mesh is cut ONCE, at table creation, into spatially
-// compact blocks of 32 points (k-d median splits, points stored block-sorted with the permutation back to the
-// original index).  Per pose:
+// compact blocks of 32 points, each made of four compact sub-blocks of 8 (k-d median splits, points stored
+// block-sorted with the permutation back to the original index).  A pred block is the 32 points of a warp; the
+// gt cloud is skipped in sub-blocks of 8 (two quads): the pair work left over goes with (rA + rB + d)^2, so the
+// smaller gt spheres save ~40 % of it against 32-point gt blocks.  Per pose:
 //   B'  one warp per block: lane l transforms point l of the block by both poses (the very xform_point calls of
 //       kernel (b): same coordinates, bit for bit), writes the gt cloud (quads) and the pred cloud to shared
-//       memory, the ADD distance at the ORIGINAL index, and the block's two bounding spheres: centre = the
-//       transformed model-space centroid, radius = the largest distance of an actual transformed point to it
-//       (a warp maximum; no assumption about R being orthonormal -- _quat_to_mat does not normalise);
+//       memory, the ADD distance at the ORIGINAL index, and the bounding spheres -- of the pred block and of the
+//       four gt sub-blocks: centre = the transformed model-space centroid, radius = the largest distance of an
+//       actual transformed point to it (no assumption about R being orthonormal -- _quat_to_mat does not normalise);
 //   C'  one warp per pred block A, one pred point per lane: the same-index gt block first (for a prediction
-//       anywhere near the truth that is where the neighbours are), then every lane tests one other gt block B,
+//       anywhere near the truth that is where the neighbours are), then every lane tests one other gt sub-block B,
 //       |cA - cB| >= sqrt(max_i m_i) + rA + rB   (with margins far above the float32 error of either side:
 //       1e-4 relative against < 1e-6), and the warp evaluates the blocks that are left.  A skipped block holds no
 //       pair with  s_ij < m_i  for any lane, and m_i only decreases, so the final minimum is the all-pairs minimum.
@@ -36,8 +38,9 @@ namespace p6d {
 constexpr int PR_T = 256;                 // threads per CTA (8 warps)
 constexpr int PR_WARPS = PR_T / 32;
 constexpr int PR_BLOCK = 32;              // points per block = lanes per warp
+constexpr int PR_SUB = 8;                 // points per gt sub-block (two quads)
 constexpr float PR_SENTINEL = 1.0e18f;    // padded gt coordinate: never the minimum (as in kernel (b))
-constexpr int PR_MIN_POINTS = 768;        // largest mesh of a table below this: the all-pairs kernel is the faster one
+constexpr int PR_MIN_POINTS = 384;        // largest mesh of a table below this: the all-pairs kernel is the faster one
 
 // per-object description of the block-sorted copy of the mesh (device + host)
 struct PrunedSlot {
@@ -48,10 +51,11 @@ struct PrunedSlot {
 // layout of one object's block (floats), Np = 32 * nb, nbp = nb rounded up to 4:
 //   x[Np] y[Np] z[Np]   block-sorted coordinates (padding of the last block repeats its first point)
 //   cx[nbp] cy[nbp] cz[nbp]   model-space centroid of every block
+//   sx[4 nb] sy[4 nb] sz[4 nb]   model-space centroid of every sub-block
 //   perm[Np] as uint16  original index of sorted position p (0xffff = padding)
 __host__ __device__ inline int pr_floats(int nb) {
     const int np = PR_BLOCK * nb, nbp = (nb + 3) / 4 * 4;
-    return 3 * np + 3 * nbp + np / 2;
+    return 3 * np + 3 * nbp + 12 * nb + np / 2;
 }
 
 struct PrunedTable {
@@ -66,9 +70,10 @@ struct PrunedTable {
 static std::mutex g_pr_mu;
 static std::map<const p6d_mesh_table*, PrunedTable*> g_pr_tables;
 
-// k-d median splits: idx[lo, hi) -> blocks of 32 consecutive entries, each spatially compact
+// k-d median splits: idx[lo, hi) -> blocks of 32 consecutive entries made of sub-blocks of 8, each spatially compact
 static void kd_split(const float* xyz, std::vector<int>& idx, int lo, int hi) {
-    if (hi - lo <= PR_BLOCK) return;
+    if (hi - lo <= PR_SUB) return;
+    const int unit = hi - lo > PR_BLOCK ? PR_BLOCK : PR_SUB;
     float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
     for (int i = lo; i < hi; ++i)
         for (int c = 0; c < 3; ++c) {
@@ -79,8 +84,8 @@ static void kd_split(const float* xyz, std::vector<int>& idx, int lo, int hi) {
     int axis = 0;
     for (int c = 1; c < 3; ++c)
         if (mx[c] - mn[c] > mx[axis] - mn[axis]) axis = c;
-    const int blocks = (hi - lo + PR_BLOCK - 1) / PR_BLOCK;
-    const int mid = lo + (blocks + 1) / 2 * PR_BLOCK;     // a multiple of 32 from lo: blocks never straddle a split
+    const int blocks = (hi - lo + unit - 1) / unit;
+    const int mid = lo + (blocks + 1) / 2 * unit;         // a multiple of 32 (8) from lo: (sub-)blocks never straddle a split
     auto key = [&](int i) { const float v = xyz[3 * i + axis]; return v == v ? v : 3.0e38f; };   // NaN sorts last
     std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
         const float va = key(a), vb = key(b);
@@ -116,7 +121,9 @@ static PrunedTable* build_pruned(const p6d_mesh_table* t, const float* xyz, cons
         const int np = PR_BLOCK * ps.nb, nbp = (ps.nb + 3) / 4 * 4;
         float* x = buf.data() + ps.offset;
         float* cen = x + 3 * np;
-        uint16_t* perm = reinterpret_cast<uint16_t*>(cen + 3 * nbp);
+        float* sub = cen + 3 * nbp;
+        const int ns = 4 * ps.nb;
+        uint16_t* perm = reinterpret_cast<uint16_t*>(sub + 3 * ns);
         for (int b = 0; b < ps.nb; ++b) {
             double c[3] = {0.0, 0.0, 0.0};
             const int cnt = std::min(PR_BLOCK, n - PR_BLOCK * b);
@@ -129,6 +136,16 @@ static PrunedTable* build_pruned(const p6d_mesh_table* t, const float* xyz, cons
                     for (int k = 0; k < 3; ++k) c[k] += src[3 * i + k];
             }
             for (int k = 0; k < 3; ++k) cen[k * nbp + b] = static_cast<float>(c[k] / cnt);
+            for (int q = 0; q < PR_BLOCK / PR_SUB; ++q) {
+                double sc[3] = {0.0, 0.0, 0.0};
+                const int first = PR_BLOCK * b + PR_SUB * q;
+                const int scnt = std::max(0, std::min(PR_SUB, n - first));
+                for (int l = 0; l < scnt; ++l)
+                    for (int k = 0; k < 3; ++k) sc[k] += x[k * np + first + l];
+                // an empty sub-block (padding only) takes the block's first point: its sphere has radius 0
+                for (int k = 0; k < 3; ++k)
+                    sub[k * ns + 4 * b + q] = scnt > 0 ? static_cast<float>(sc[k] / scnt) : x[k * np + PR_BLOCK * b];
+            }
         }
     }
     if (cudaMalloc(&pt->d_sorted, buf.size() * sizeof(float)) != cudaSuccess ||
@@ -169,7 +186,7 @@ struct PrunedArgs {
 // dadd | dadds | pred spheres | gt spheres
 __host__ __device__ inline size_t pr_smem_floats(int nb, int nmax) {
     const int np = PR_BLOCK * nb;
-    return static_cast<size_t>(pr_floats(nb)) + 3 * np + 3 * np + 2 * static_cast<size_t>((nmax + 3) / 4 * 4) + 8 * nb;
+    return static_cast<size_t>(pr_floats(nb)) + 3 * np + 3 * np + 2 * static_cast<size_t>((nmax + 3) / 4 * 4) + 4 * nb + 16 * nb;
 }
 
 // one gt block (8 quads) against the lane's pred point
@@ -195,7 +212,33 @@ __device__ __forceinline__ float eval_block(const float4* __restrict__ q, float 
     return min_nan(m, m2);
 }
 
-__global__ void __launch_bounds__(PR_T, 3) adds_pruned_kernel(EvalArgs a, PrunedArgs pa, int nb_max, int nmax) {
+// one gt sub-block (2 quads) against the lane's pred point
+__device__ __forceinline__ float eval_sub(const float4* __restrict__ q, float px, float py, float pz, float m) {
+    const float2 pxx = make_float2(px, px), pyy = make_float2(py, py), pzz = make_float2(pz, pz);
+    float m2 = __int_as_float(0x7f800000);
+#pragma unroll
+    for (int k = 0; k < PR_SUB / 4; ++k) {
+        const float4 X = q[3 * k], Y = q[3 * k + 1], Z = q[3 * k + 2];
+        {
+            const float2 dx = sub2(pxx, make_float2(X.x, X.y)), dy = sub2(pyy, make_float2(Y.x, Y.y)),
+                         dz = sub2(pzz, make_float2(Z.x, Z.y));
+            const float2 s = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            m = min3_nan(m, s.x, s.y);
+        }
+        {
+            const float2 dx = sub2(pxx, make_float2(X.z, X.w)), dy = sub2(pyy, make_float2(Y.z, Y.w)),
+                         dz = sub2(pzz, make_float2(Z.z, Z.w));
+            const float2 s = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+            m2 = min3_nan(m2, s.x, s.y);
+        }
+    }
+    return min_nan(m, m2);
+}
+
+// MINB = CTAs per SM the register budget is sized for: 3 (<= 80 registers) for tables whose shared memory allows
+// no more anyway, 4 (64 registers, one spilled word) for small meshes
+template <int MINB>
+__global__ void __launch_bounds__(PR_T, MINB) adds_pruned_kernel(EvalArgs a, PrunedArgs pa, int nb_max, int nmax) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int np_max = PR_BLOCK * nb_max;
     float* s_sorted = reinterpret_cast<float*>(smem_raw);
@@ -204,7 +247,7 @@ __global__ void __launch_bounds__(PR_T, 3) adds_pruned_kernel(EvalArgs a, Pruned
     float* s_dadd = s_pred + 3 * np_max;
     float* s_dadds = s_dadd + (nmax + 3) / 4 * 4;
     float4* s_cp = reinterpret_cast<float4*>(s_dadds + (nmax + 3) / 4 * 4);
-    float4* s_cg = s_cp + nb_max;
+    float4* s_cg = s_cp + nb_max;                // gt spheres, one per sub-block: [4 * nb_max]
     __shared__ uint64_t s_bar;
     __shared__ float s_pose[14];
     __shared__ float s_mean[2];
@@ -265,7 +308,9 @@ __global__ void __launch_bounds__(PR_T, 3) adds_pruned_kernel(EvalArgs a, Pruned
         const float* my = mx + np;
         const float* mz = my + np;
         const float* cen = mz + np;
-        const uint16_t* perm = reinterpret_cast<const uint16_t*>(cen + 3 * nbp);
+        const float* sub = cen + 3 * nbp;
+        const int ns = 4 * nb;
+        const uint16_t* perm = reinterpret_cast<const uint16_t*>(sub + 3 * ns);
         const int mode = s.xform_mode;
 
         // phase B': the warp's blocks -> both clouds, ADD distances, bounding spheres
@@ -296,26 +341,29 @@ __global__ void __launch_bounds__(PR_T, 3) adds_pruned_kernel(EvalArgs a, Pruned
                 if (valid) s_dadd[orig] = __fsqrt_rn(sq3(__fsub_rn(px, qx), __fsub_rn(py, qy), __fsub_rn(pz, qz)));
                 // spheres: centre = the transformed centroid (any point would do), radius from the actual points
                 const float cx = cen[blk], cy = cen[nbp + blk], cz = cen[2 * nbp + blk];
+                const int sb = 4 * blk + (lane >> 3);
+                const float sx = sub[sb], sy = sub[ns + sb], sz = sub[2 * ns + sb];
                 float cpx, cpy, cpz, cgx, cgy, cgz;
-                xform_point(XF_FMA_CHAIN, cx, cy, cz, Rp, tp, cpx, cpy, cpz);
-                xform_point(XF_FMA_CHAIN, cx, cy, cz, Rg, tg, cgx, cgy, cgz);
+                xform_point(XF_FMA_CHAIN, cx, cy, cz, Rp, tp, cpx, cpy, cpz);     // pred: the whole block
+                xform_point(XF_FMA_CHAIN, sx, sy, sz, Rg, tg, cgx, cgy, cgz);     // gt: the lane's sub-block
                 const float dp = sqrtf(sq3(px - cpx, py - cpy, pz - cpz));
                 const float dg = sqrtf(sq3(qx - cgx, qy - cgy, qz - cgz));
-                // maximum over the valid lanes through the bit patterns (non-negative floats order like unsigned
+                // maxima over the valid lanes through the bit patterns (non-negative floats order like unsigned
                 // integers; a NaN sorts above every number and so survives into the radius)
                 const unsigned rp = __reduce_max_sync(full, valid ? __float_as_uint(dp) : 0u);
-                const unsigned rg = __reduce_max_sync(full, valid ? __float_as_uint(dg) : 0u);
-                if (lane == 0) {
-                    s_cp[blk] = make_float4(cpx, cpy, cpz, __uint_as_float(rp) * 1.00001f);
-                    s_cg[blk] = make_float4(cgx, cgy, cgz, __uint_as_float(rg) * 1.00001f);
-                }
+                unsigned rg = valid ? __float_as_uint(dg) : 0u;
+                rg = max(rg, __shfl_xor_sync(full, rg, 1));
+                rg = max(rg, __shfl_xor_sync(full, rg, 2));
+                rg = max(rg, __shfl_xor_sync(full, rg, 4));
+                if (lane == 0) s_cp[blk] = make_float4(cpx, cpy, cpz, __uint_as_float(rp) * 1.00001f);
+                if ((lane & 7) == 0) s_cg[sb] = make_float4(cgx, cgy, cgz, __uint_as_float(rg) * 1.00001f);
             }
         }
         __syncthreads();  // (B)
 
         // phase C': one warp per pred block, one pred point per lane
         {
-            const float4* gq4 = reinterpret_cast<const float4*>(s_gt);      // block B at gq4[24 B .. 24 B + 23]
+            const float4* gq4 = reinterpret_cast<const float4*>(s_gt);      // block B at gq4[24 B ..], sub-block at gq4[6 SB ..]
             for (int A = warp; A < nb; A += PR_WARPS) {
                 const int p = PR_BLOCK * A + lane;
                 const unsigned orig = perm[p];
@@ -323,13 +371,13 @@ __global__ void __launch_bounds__(PR_T, 3) adds_pruned_kernel(EvalArgs a, Pruned
                 const float px = s_pred[p], py = s_pred[np + p], pz = s_pred[2 * np + p];
                 float m = eval_block(gq4 + 24 * A, px, py, pz, __int_as_float(0x7f800000));
                 const float4 cA = s_cp[A];
-                for (int c0 = 0; c0 < nb; c0 += 32) {
-                    // the bound uses the current minima: recomputed per chunk of 32 candidate blocks
+                for (int c0 = 0; c0 < ns; c0 += 32) {
+                    // the bound uses the current minima: recomputed per chunk of 32 candidate sub-blocks
                     const float mmax = __uint_as_float(__reduce_max_sync(full, valid ? __float_as_uint(m) : 0u));
                     const float th = sqrtf(mmax) * 1.0001f + cA.w;
                     const int Bq = c0 + lane;
                     bool cand = false;
-                    if (Bq < nb && Bq != A) {
+                    if (Bq < ns && (Bq >> 2) != A) {
                         const float4 cB = s_cg[Bq];
                         const float dx = cA.x - cB.x, dy = cA.y - cB.y, dz = cA.z - cB.z;
                         const float d2 = dx * dx + dy * dy + dz * dz;
@@ -339,7 +387,7 @@ __global__ void __launch_bounds__(PR_T, 3) adds_pruned_kernel(EvalArgs a, Pruned
                         cand = !skip;
                     }
                     for (unsigned todo = __ballot_sync(full, cand); todo; todo &= todo - 1)
-                        m = eval_block(gq4 + 24 * (c0 + __ffs(todo) - 1), px, py, pz, m);
+                        m = eval_sub(gq4 + 6 * (c0 + __ffs(todo) - 1), px, py, pz, m);
                 }
                 // sqrt is monotone and correctly rounded: sqrt(min s) == min sqrt(s)
                 if (valid) s_dadds[orig] = __fsqrt_rn(m);
@@ -400,7 +448,8 @@ int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaSt
                           table->max_count, (limit - 1024) / 4 / 12 / 32 * 32);
                 return P6D_ETOOBIG;
             }
-            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             cur = smem;
         }
     }
@@ -408,12 +457,17 @@ int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaSt
     a.work_counter = table->d_counters + (__atomic_fetch_add(&table->counter_idx, 1u, __ATOMIC_RELAXED) % P6D_NUM_COUNTERS);
     P6D_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
     int per_sm = 0;
-    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel, PR_T, smem));
+    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<4>, PR_T, smem));
+    const bool four = per_sm >= 4;          // small meshes: shared memory leaves room for the 64-register instantiation (+5-8 %)
+    if (!four) P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<3>, PR_T, smem));
     if (per_sm < 1) per_sm = 1;
     int64_t grid = static_cast<int64_t>(table->sm_count) * per_sm;
     if (grid > a.B) grid = a.B;
     PrunedArgs pa{ptab->d_sorted, ptab->d_slots};
-    adds_pruned_kernel<<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
+    if (four)
+        adds_pruned_kernel<4><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
+    else
+        adds_pruned_kernel<3><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
     P6D_CUDA(cudaGetLastError());
     *used = true;
     return P6D_OK;

@@ -675,12 +675,13 @@ def run_b200(args):
                   "value": world * B * args.steps / (float(pms.item()) * 1e-3), "unit": UNIT, "workload": "the config-2 step above",
                   "ms_per_step": float(pms.item()) / args.steps, "outputs_equal_all_pairs": bool(eq.item()),
                   "speedup_vs_all_pairs": (world * B * args.steps / (float(pms.item()) * 1e-3)) / value}
-        if sweeps.get("n2048") is not None:
-            ps = sweep_record(pkg, dev, rank, world, 2048, args.sweep_per_block, args.sweep_check, barrier, exact_pruning=True)
-            pruned["sweep_n2048"] = {k: ps[k] for k in ("seconds", "device_seconds", "poses_per_s", "hits_per_variant",
+        for key, full_rec in sweeps.items():       # the config-5 sweeps again, with the switch on
+            ps = sweep_record(pkg, dev, rank, world, full_rec["n_points"], args.sweep_per_block, args.sweep_check, barrier,
+                              exact_pruning=True)
+            pruned[f"sweep_{key}"] = {k: ps[k] for k in ("seconds", "device_seconds", "poses_per_s", "hits_per_variant",
                                                          "hits_table_sha256", "oracle_check", "adds_kernel")}
-            pruned["sweep_n2048"]["hits_table_equals_all_pairs"] = ps["hits_table_sha256"] == sweeps["n2048"]["hits_table_sha256"]
-            pruned["sweep_n2048"]["speedup_vs_all_pairs"] = sweeps["n2048"]["seconds"] / ps["seconds"]
+            pruned[f"sweep_{key}"]["hits_table_equals_all_pairs"] = ps["hits_table_sha256"] == full_rec["hits_table_sha256"]
+            pruned[f"sweep_{key}"]["speedup_vs_all_pairs"] = full_rec["seconds"] / ps["seconds"]
         del ptable
 
     if rank == 0:
