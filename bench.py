@@ -89,7 +89,10 @@ def profiled_traffic():
     committed `ncu --set full` summary under profiles/ (same workload and launch shape as the bench)."""
     import glob, re
     best = None
-    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "adds_*_summary.txt"))):
+    def capture_order(path):       # adds_r2l < adds_r2ag: round number, then the visit tag a..z, aa..az
+        m = re.search(r"adds_r(\d+)([a-z]*)_", os.path.basename(path))
+        return (int(m.group(1)), len(m.group(2)), m.group(2)) if m else (0, 0, "")
+    for path in sorted(glob.glob(os.path.join(REPO, "profiles", "adds_*_summary.txt")), key=capture_order):
         txt = open(path).read()
         r = re.search(r"dram__bytes_read\.sum\s+([0-9.]+)\s+(\w+)", txt)
         w = re.search(r"dram__bytes_write\.sum\s+([0-9.]+)\s+(\w+)", txt)

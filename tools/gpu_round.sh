@@ -18,6 +18,6 @@ for step in "$@"; do
             BARGS="--no-sweep --no-pruned --no-secondary --no-cpu-baseline --no-microbench"
             timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv python bench.py --steps 2 --warmup 3 $BARGS > $OUT/${TAG}_ncu_launches.log 2>&1; echo "launch list rc=$?"
             timeout 400 ncu --set full --clock-control none --import-source on -k regex:adds_cta --launch-skip 3 -c 1 -f -o $OUT/adds_${TAG} python bench.py --steps 2 --warmup 3 $BARGS > $OUT/${TAG}_ncu_adds.log 2>&1; echo "adds capture rc=$?"
-            timeout 600 ncu --set full --clock-control none --import-source on -k regex:'add_pose|pose_loss|pinhole|depth|add_backward|quat|tf32|synth|adds_cta' -f -o $OUT/secondary_${TAG} python tools/profile_small.py > $OUT/${TAG}_ncu_secondary.log 2>&1; echo "secondary capture rc=$?"; tail -2 $OUT/${TAG}_ncu_secondary.log ;;
+            timeout 600 ncu --set full --clock-control none --import-source on -k regex:'add_pose|pose_loss|pinhole|depth|detection|add_backward|quat|tf32|synth|adds_cta|adds_pruned' -f -o $OUT/secondary_${TAG} python tools/profile_small.py > $OUT/${TAG}_ncu_secondary.log 2>&1; echo "secondary capture rc=$?"; tail -2 $OUT/${TAG}_ncu_secondary.log ;;
   esac
 done

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One launch of every secondary kernel at the sizes quoted in DESIGN.md (for ncu):
-   ncu --set full --clock-control none -k regex:'add_pose|pose_loss|pinhole|depth|add_backward|quat|tf32|synth|adds_cta' -o gpurun_out/secondary python tools/profile_small.py"""
+   ncu --set full --clock-control none -k regex:'add_pose|pose_loss|pinhole|depth|detection|add_backward|quat|tf32|synth|adds_cta|adds_pruned' -o gpurun_out/secondary python tools/profile_small.py"""
 import importlib, os, sys, tempfile
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -62,5 +62,12 @@ t2 = core.MeshTable(pts2, dia2, pkg.SYMMETRIC_OBJECT_IDS, dev)
 c2 = [T(x) for x in W.config2(2048)]
 out = torch.empty(2048, dtype=torch.float32, device=dev)
 core.check(core.lib().p6d_adds_tf32_eval(t2.handle, *(core.ptr(x) for x in c2), 2048, 3, core.ptr(out), 0, core.stream_ptr(dev)))
+# N1, inference form (xyxy detector boxes): 256 boxes and 1 M boxes of one frame
+xyxy = boxes.copy(); xyxy[:, 2:] += xyxy[:, :2]
+pkg.detection_backproject(T(frame), T(xyxy))
+pkg.detection_backproject(T(frame), T(np.tile(xyxy, (4096, 1))))
+# (b') the opt-in exact-pruned ADD-S kernel on 16,384 config-2 poses
+c16 = [T(x) for x in W.config2(16384)]
+t2.evaluate(*c16, prune=True)
 torch.cuda.synchronize()
 print("profile_small done")
