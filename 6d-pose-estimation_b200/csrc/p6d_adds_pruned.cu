@@ -235,6 +235,15 @@ __device__ __forceinline__ float eval_sub(const float4* __restrict__ q, float px
     return min_nan(m, m2);
 }
 
+// two gt sub-blocks at once: twice the independent chains for the same instructions (the candidate loop is serial
+// in m otherwise, and at 2 CTAs per SM there are only 4 warps per scheduler to hide it)
+__device__ __forceinline__ float eval_two(const float4* __restrict__ q0, const float4* __restrict__ q1, float px, float py,
+                                          float pz, float m) {
+    const float a = eval_sub(q0, px, py, pz, m);
+    const float b = eval_sub(q1, px, py, pz, __int_as_float(0x7f800000));
+    return min_nan(a, b);
+}
+
 // MINB = CTAs per SM the register budget is sized for: 3 (<= 80 registers) for tables whose shared memory allows
 // no more anyway, 4 (64 registers, one spilled word) for small meshes
 template <int MINB>
@@ -253,13 +262,17 @@ __global__ void __launch_bounds__(PR_T, MINB) adds_pruned_kernel(EvalArgs a, Pru
     __shared__ float s_mean[2];
     __shared__ long long s_oid;
     __shared__ int s_next;
+    __shared__ int s_blk[2];    // pred blocks of phase C' are claimed warp by warp (double-buffered across poses)
 
     const unsigned full = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_mbar_init();
+        s_blk[0] = PR_WARPS;
+        s_blk[1] = PR_WARPS;
     }
+    int par = 0;
     long long staged_oid = -1;
     uint32_t phase = 0;
     // dynamic pose scheduler, one pose ahead (see adds_cta_kernel)
@@ -364,7 +377,10 @@ __global__ void __launch_bounds__(PR_T, MINB) adds_pruned_kernel(EvalArgs a, Pru
         // phase C': one warp per pred block, one pred point per lane
         {
             const float4* gq4 = reinterpret_cast<const float4*>(s_gt);      // block B at gq4[24 B ..], sub-block at gq4[6 SB ..]
-            for (int A = warp; A < nb; A += PR_WARPS) {
+            // the number of sub-blocks left over differs from block to block: the first block of a warp is its own
+            // index, the next ones are claimed from a counter, so no warp waits at barrier (C) for a slow one
+            int A = warp;
+            while (A < nb) {
                 const int p = PR_BLOCK * A + lane;
                 const unsigned orig = perm[p];
                 const bool valid = orig != 0xffffu;
@@ -386,14 +402,29 @@ __global__ void __launch_bounds__(PR_T, MINB) adds_pruned_kernel(EvalArgs a, Pru
                         const bool skip = d2 * 0.9999f >= rhs * rhs && d2 < 3.0e38f;
                         cand = !skip;
                     }
-                    for (unsigned todo = __ballot_sync(full, cand); todo; todo &= todo - 1)
-                        m = eval_sub(gq4 + 6 * (c0 + __ffs(todo) - 1), px, py, pz, m);
+                    unsigned todo = __ballot_sync(full, cand);
+                    while (todo) {
+                        const int b0 = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        if (todo) {
+                            const int b1 = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            m = eval_two(gq4 + 6 * (c0 + b0), gq4 + 6 * (c0 + b1), px, py, pz, m);
+                        } else {
+                            m = eval_sub(gq4 + 6 * (c0 + b0), px, py, pz, m);
+                        }
+                    }
                 }
                 // sqrt is monotone and correctly rounded: sqrt(min s) == min sqrt(s)
                 if (valid) s_dadds[orig] = __fsqrt_rn(m);
+                int nxt = 0;
+                if (lane == 0) nxt = atomicAdd(&s_blk[par], 1);
+                A = __shfl_sync(full, nxt, 0);
             }
         }
         __syncthreads();  // (C)
+        if (tid == 0) s_blk[par] = PR_WARPS;      // re-armed for the pose after the next; nobody reads it before barrier (A)
+        par ^= 1;
 
         // phase D: ordered means (ATen summation order) on warps 0 and 1, decision, outputs
         if (tid < 64) {
@@ -448,6 +479,7 @@ int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaSt
                           table->max_count, (limit - 1024) / 4 / 12 / 32 * 32);
                 return P6D_ETOOBIG;
             }
+            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             cur = smem;
@@ -456,18 +488,28 @@ int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaSt
     EvalArgs a = args;
     a.work_counter = table->d_counters + (__atomic_fetch_add(&table->counter_idx, 1u, __ATOMIC_RELAXED) % P6D_NUM_COUNTERS);
     P6D_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
-    int per_sm = 0;
+    // the instantiation whose register budget matches what shared memory lets be resident: 4 CTAs per SM
+    // (64 registers) for small meshes (+5-8 %), 3 (<= 80), or 2 (<= 128) at 2,048 points
+    int per_sm = 0, minb = 4;
     P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<4>, PR_T, smem));
-    const bool four = per_sm >= 4;          // small meshes: shared memory leaves room for the 64-register instantiation (+5-8 %)
-    if (!four) P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<3>, PR_T, smem));
+    if (per_sm < 4) {
+        minb = 3;
+        P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<3>, PR_T, smem));
+        if (per_sm < 3) {
+            minb = 2;
+            P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<2>, PR_T, smem));
+        }
+    }
     if (per_sm < 1) per_sm = 1;
     int64_t grid = static_cast<int64_t>(table->sm_count) * per_sm;
     if (grid > a.B) grid = a.B;
     PrunedArgs pa{ptab->d_sorted, ptab->d_slots};
-    if (four)
+    if (minb == 4)
         adds_pruned_kernel<4><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
-    else
+    else if (minb == 3)
         adds_pruned_kernel<3><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
+    else
+        adds_pruned_kernel<2><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
     P6D_CUDA(cudaGetLastError());
     *used = true;
     return P6D_OK;
