@@ -433,6 +433,15 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
         table = core.MeshTable(pts, {0: 0.102}, pkg.SYMMETRIC_OBJECT_IDS, dev)
         t = timed(lambda: table.evaluate_packed(qb, tb, qa, ta, obj, want_adds=False), 5)
         fp32_row(f"add_pose_kernel (a), ADD only, N={npts}", m, 46 * npts, t, hbm_gbs=m * 73 / t / 1e9)
+    # the several-mesh form of kernel (a): the 13 LineMOD-sized meshes of the sweep, poses sorted by object
+    pts13, dia13 = W.sweep_meshes(500)
+    t13 = core.MeshTable(pts13, dia13, pkg.SYMMETRIC_OBJECT_IDS, dev)
+    ids13 = torch.tensor(sorted(pts13), dtype=torch.int64, device=dev)
+    obj13 = ids13[torch.arange(m, device=dev) % len(pts13)]
+    ord13 = torch.argsort(obj13, stable=True).to(torch.int32)
+    t = timed(lambda: t13.evaluate_packed(qb, tb, qa, ta, obj13, want_adds=False, order=ord13), 5)
+    fp32_row("add_pose_kernel (a), ADD only, table of 13 meshes x 500 points, poses ordered by object", m, 46 * 500, t,
+             hbm_gbs=m * 77 / t / 1e9)
     for npts, Bn in ((500, 1 << 20), (1000, 1 << 18)):
         pts = {9: W.box_mesh(npts, (0.1, 0.12, 0.05), 200 + npts)}
         tb_ = core.MeshTable(pts, {9: 0.1646}, pkg.SYMMETRIC_OBJECT_IDS, dev)
