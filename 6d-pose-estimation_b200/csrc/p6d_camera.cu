@@ -8,6 +8,9 @@
 // Elementwise, HBM/latency-bound: one thread per row, K read as scalars (4 of the 9
 // entries), everything else coalesced.  Operation order is the reference's:
 // ((u - cx) * z) / fx with an IEEE division.
+#include <map>
+#include <mutex>
+
 #include "p6d_common.cuh"
 
 namespace p6d {
@@ -40,23 +43,42 @@ __global__ void __launch_bounds__(CAM_T) pinhole_fwd_kernel(const float* __restr
 // Shared [3,3] K (the reference's common case): 24 B per row, nothing but z, the centre and the
 // output.  One row per thread writes its three floats with stride-12 scalar stores -- three store
 // instructions that each touch every sector of the warp's 384 bytes (measured 3.9 TB/s = 60 % of HBM).
-// Four rows per thread: z as one float4, the centres as two, the output as three -- every access a
-// full 16-byte vector.  Same arithmetic per row.
+// Four rows per thread: z as one float4, the centres as two, the output as three 16-byte vectors (72 %).
+// The three vectors of a lane are 48 bytes apart, so each store instruction still fills only half of every
+// 32-byte sector it touches; the warp therefore passes its 1,536 output bytes through shared memory (12-word
+// lane stride: conflict-free for 128-bit accesses) and stores them as three fully coalesced 512-byte rows.
+// Same arithmetic per row.
 __global__ void __launch_bounds__(CAM_T) pinhole_fwd_shared4_kernel(const float4* __restrict__ z4,
                                                                     const float4* __restrict__ uv4,
                                                                     const float* __restrict__ K, int64_t B4,
                                                                     float4* __restrict__ out4) {
+    __shared__ float4 s_out[CAM_T / 32][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* so = s_out[warp];
     const float fx = __ldg(K + 0), cx = __ldg(K + 2), fy = __ldg(K + 4), cy = __ldg(K + 5);
-    for (int64_t q = (int64_t)blockIdx.x * CAM_T + threadIdx.x; q < B4; q += (int64_t)gridDim.x * CAM_T) {
-        const float4 zz = z4[q];
-        const float4 c0 = uv4[2 * q], c1 = uv4[2 * q + 1];          // (u0,v0,u1,v1), (u2,v2,u3,v3)
-        const float x0 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.x, cx), zz.x), fx), y0 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.y, cy), zz.x), fy);
-        const float x1 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.z, cx), zz.y), fx), y1 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.w, cy), zz.y), fy);
-        const float x2 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.x, cx), zz.z), fx), y2 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.y, cy), zz.z), fy);
-        const float x3 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.z, cx), zz.w), fx), y3 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.w, cy), zz.w), fy);
-        out4[3 * q + 0] = make_float4(x0, y0, zz.x, x1);
-        out4[3 * q + 1] = make_float4(y1, zz.y, x2, y2);
-        out4[3 * q + 2] = make_float4(zz.z, x3, y3, zz.w);
+    // whole warps only: the loop bound is per warp so that every lane reaches the __syncwarp()s
+    const int64_t stride = (int64_t)gridDim.x * CAM_T;
+    for (int64_t q0 = (int64_t)blockIdx.x * CAM_T + warp * 32; q0 < B4; q0 += stride) {
+        const int64_t q = q0 + lane;
+        const bool live = q < B4;
+        if (live) {
+            const float4 zz = z4[q];
+            const float4 c0 = uv4[2 * q], c1 = uv4[2 * q + 1];          // (u0,v0,u1,v1), (u2,v2,u3,v3)
+            const float x0 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.x, cx), zz.x), fx), y0 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.y, cy), zz.x), fy);
+            const float x1 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.z, cx), zz.y), fx), y1 = __fdiv_rn(__fmul_rn(__fsub_rn(c0.w, cy), zz.y), fy);
+            const float x2 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.x, cx), zz.z), fx), y2 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.y, cy), zz.z), fy);
+            const float x3 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.z, cx), zz.w), fx), y3 = __fdiv_rn(__fmul_rn(__fsub_rn(c1.w, cy), zz.w), fy);
+            so[3 * lane + 0] = make_float4(x0, y0, zz.x, x1);
+            so[3 * lane + 1] = make_float4(y1, zz.y, x2, y2);
+            so[3 * lane + 2] = make_float4(zz.z, x3, y3, zz.w);
+        }
+        __syncwarp();
+        const int64_t left = B4 - q0;                                  // rows-of-four of this warp that exist
+        const int vecs = left >= 32 ? 96 : (int)(3 * left);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            if (32 * k + lane < vecs) out4[3 * q0 + 32 * k + lane] = so[32 * k + lane];
+        __syncwarp();
     }
 }
 
@@ -332,11 +354,30 @@ __global__ void __launch_bounds__(CAM_T) project_points_kernel(const double* __r
     }
 }
 
-static int grid_for(int64_t B, int device, unsigned* grid) {
+// Grid of a grid-stride kernel: one thread per row up to what is RESIDENT at once.  Every block of a grid-stride
+// loop runs the same number of trips, so blocks beyond the resident set form a second, thinly occupied wave that
+// takes as long as the first (the 40-register shared-K pinhole kernel fits 6 blocks per SM: a fixed cap of 8 per
+// SM ran 1.33 waves and reached 72 % of HBM).  Occupancy is asked once per kernel.
+template <class Kernel>
+static int grid_for(Kernel kernel, int64_t B, int device, unsigned* grid) {
+    static std::mutex mu;
+    static std::map<const void*, int> cache;        // kernels of one signature share this instantiation: key by address
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(reinterpret_cast<const void*>(kernel));
+        if (it != cache.end()) per_sm = it->second;
+    }
+    if (per_sm == 0) {
+        P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CAM_T, 0));
+        if (per_sm < 1) per_sm = 1;
+        std::lock_guard<std::mutex> lock(mu);
+        cache[reinterpret_cast<const void*>(kernel)] = per_sm;
+    }
     int sms = 0;
     P6D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     int64_t blocks = (B + CAM_T - 1) / CAM_T;
-    const int64_t cap = (int64_t)sms * 8;
+    const int64_t cap = (int64_t)sms * per_sm;
     *grid = (unsigned)(blocks > cap ? cap : blocks);
     return P6D_OK;
 }
@@ -360,7 +401,7 @@ int p6d_pinhole_fwd(const float* z, const float* uv, const float* K, int k_batch
                      ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(uv) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
     if (vec) {       // four rows per thread, 16-byte accesses; the last B % 4 rows go through the scalar kernel
         const int64_t B4 = B / 4, done = 4 * B4;
-        int rc = grid_for(B4, device, &grid);
+        int rc = grid_for(pinhole_fwd_shared4_kernel, B4, device, &grid);
         if (rc) return rc;
         pinhole_fwd_shared4_kernel<<<grid, CAM_T, 0, st>>>(reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(uv),
                                                          K, B4, reinterpret_cast<float4*>(out));
@@ -371,7 +412,7 @@ int p6d_pinhole_fwd(const float* z, const float* uv, const float* K, int k_batch
         }
         return P6D_OK;
     }
-    int rc = grid_for(B, device, &grid);
+    int rc = grid_for(pinhole_fwd_kernel, B, device, &grid);
     if (rc) return rc;
     pinhole_fwd_kernel<<<grid, CAM_T, 0, st>>>(z, uv, K, k_batched, B, out);
     P6D_CUDA(cudaGetLastError());
@@ -386,7 +427,7 @@ int p6d_pinhole_bwd(const float* grad_out, const float* uv, const float* K, int 
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     unsigned grid;
-    int rc = grid_for(B, device, &grid);
+    int rc = grid_for(pinhole_bwd_kernel, B, device, &grid);
     if (rc) return rc;
     pinhole_bwd_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(grad_out, uv, K, k_batched, B, grad_z);
     P6D_CUDA(cudaGetLastError());
@@ -411,7 +452,7 @@ int p6d_depth_backproject(const float* depth, int H, int W, const float* uv, con
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     unsigned grid;
-    int rc = grid_for(B, device, &grid);
+    int rc = grid_for(depth_backproject_kernel, B, device, &grid);
     if (rc) return rc;
     depth_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(depth, H, W, uv, K, k_batched, B,
                                                                                     clamp_hi, out);
@@ -435,7 +476,7 @@ int p6d_depth_crop_backproject(const uint16_t* depth, int H, int W, const int32_
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     unsigned grid;
-    int rc = grid_for(B, device, &grid);
+    int rc = grid_for(depth_crop_backproject_kernel, B, device, &grid);
     if (rc) return rc;
     depth_crop_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
         depth, H, W, boxes, B, K, img_size, bilinear, xyz, center, kcrop, z_mm);
@@ -458,7 +499,7 @@ int p6d_detection_backproject(const uint16_t* depth, int H, int W, const int32_t
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     unsigned grid;
-    int rc = grid_for(B, device, &grid);
+    int rc = grid_for(detection_backproject_kernel, B, device, &grid);
     if (rc) return rc;
     detection_backproject_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
         depth, H, W, boxes_xyxy, B, K, img_size, xyz, center, kcrop, z_m);
@@ -476,7 +517,7 @@ int p6d_project_points(const double* points, int N, const double* rotation, int 
     DeviceGuard guard(device);
     if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
     unsigned grid;
-    int rc = grid_for(B * N, device, &grid);
+    int rc = grid_for(project_points_kernel, B * N, device, &grid);
     if (rc) return rc;
     project_points_kernel<<<grid, CAM_T, 0, static_cast<cudaStream_t>(stream)>>>(
         points, N, rotation, rotation_is_quat, translation, K, B, reinterpret_cast<long long*>(uv));
