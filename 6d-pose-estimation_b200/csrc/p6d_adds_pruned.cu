@@ -27,7 +27,9 @@
 // The squared distance of a pair is computed by the same packed instructions in the same order as kernel (b)
 // (3 FADD2, FMUL2, 2 FFMA2, FMNMX3.NAN), so every surviving value has the same bits.
 #include <algorithm>
+#include <atomic>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 
@@ -64,7 +66,7 @@ struct PrunedTable {
     std::vector<PrunedSlot> h_slots;
     int max_nb = 0;
     int max_count = 0;
-    bool enabled = false;       // p6d_mesh_table_set_pruning: launch_eval takes this kernel where the table qualifies
+    std::atomic<bool> enabled{false};   // p6d_mesh_table_set_pruning: launch_eval takes this kernel where the table qualifies
 };
 
 static std::mutex g_pr_mu;
@@ -96,7 +98,7 @@ static void kd_split(const float* xyz, std::vector<int>& idx, int lo, int hi) {
 }
 
 static PrunedTable* build_pruned(const p6d_mesh_table* t, const float* xyz, const int32_t* offsets) {
-    PrunedTable* pt = new PrunedTable();
+    std::unique_ptr<PrunedTable> pt(new PrunedTable());     // freed if anything below throws
     pt->h_slots.resize(t->n_slots);
     size_t total = 0;
     for (int s = 0; s < t->n_slots; ++s) {
@@ -156,10 +158,9 @@ static PrunedTable* build_pruned(const p6d_mesh_table* t, const float* xyz, cons
         cudaGetLastError();
         if (pt->d_sorted) cudaFree(pt->d_sorted);
         if (pt->d_slots) cudaFree(pt->d_slots);
-        delete pt;
         return nullptr;
     }
-    return pt;
+    return pt.release();
 }
 
 // called by p6d_mesh_table_destroy
@@ -463,7 +464,7 @@ int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaSt
         auto it = g_pr_tables.find(table);
         if (it != g_pr_tables.end()) ptab = it->second;
     }
-    if (!ptab || (!force && (!ptab->enabled || table->max_count < PR_MIN_POINTS))) return P6D_OK;
+    if (!ptab || (!force && (!ptab->enabled.load(std::memory_order_relaxed) || table->max_count < PR_MIN_POINTS))) return P6D_OK;
     const int nb = ptab->max_nb > 0 ? ptab->max_nb : 1;
     const size_t smem = sizeof(float) * pr_smem_floats(nb, table->max_count);
     {
@@ -525,7 +526,12 @@ extern "C" {
 // entry point then reports that the table has no blocks.
 void p6d_internal_build_pruned(const p6d_mesh_table* t, const float* xyz, const int32_t* offsets) {
     if (t->max_count > 65534) return;            // permutation is stored as uint16
-    PrunedTable* pt = build_pruned(t, xyz, offsets);
+    PrunedTable* pt = nullptr;
+    try {
+        pt = build_pruned(t, xyz, offsets);
+    } catch (...) {                              // out of host memory: the table simply has no blocks
+        return;
+    }
     if (!pt) return;
     std::lock_guard<std::mutex> lock(g_pr_mu);
     g_pr_tables[t] = pt;
@@ -543,7 +549,7 @@ int p6d_mesh_table_set_pruning(p6d_mesh_table* table, int enable) {
                   "or out of memory at creation)");
         return P6D_ETOOBIG;
     }
-    it->second->enabled = enable != 0;
+    it->second->enabled.store(enable != 0, std::memory_order_relaxed);
     return P6D_OK;
 }
 
