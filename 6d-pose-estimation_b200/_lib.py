@@ -212,7 +212,7 @@ class MeshTable:
 
     def set_pruning(self, enable=True):
         """Opt in to (or out of) the exact-pruned ADD-S kernel for this table: same bits as the all-pairs
-        kernel, taken where it pays (largest mesh >= 384 points); see include/p6d.h."""
+        kernel, taken where it pays (largest mesh >= 128 points); see include/p6d.h."""
         check(lib().p6d_mesh_table_set_pruning(self.handle, 1 if enable else 0))
         return self
 

@@ -37,12 +37,10 @@
 
 namespace p6d {
 
-constexpr int PR_T = 256;                 // threads per CTA (8 warps)
-constexpr int PR_WARPS = PR_T / 32;
 constexpr int PR_BLOCK = 32;              // points per block = lanes per warp
 constexpr int PR_SUB = 8;                 // points per gt sub-block (two quads)
 constexpr float PR_SENTINEL = 1.0e18f;    // padded gt coordinate: never the minimum (as in kernel (b))
-constexpr int PR_MIN_POINTS = 384;        // largest mesh of a table below this: the all-pairs kernel is the faster one
+constexpr int PR_MIN_POINTS = 128;        // largest mesh of a table below this: nothing to gain (1.05x at 37 points)
 
 // per-object description of the block-sorted copy of the mesh (device + host)
 struct PrunedSlot {
@@ -245,10 +243,14 @@ __device__ __forceinline__ float eval_two(const float4* __restrict__ q0, const f
     return min_nan(a, b);
 }
 
-// MINB = CTAs per SM the register budget is sized for: 3 (<= 80 registers) for tables whose shared memory allows
-// no more anyway, 4 (64 registers, one spilled word) for small meshes
-template <int MINB>
-__global__ void __launch_bounds__(PR_T, MINB) adds_pruned_kernel(EvalArgs a, PrunedArgs pa, int nb_max, int nmax) {
+// T threads per CTA = one pose per T threads; MINB = CTAs per SM the register budget is sized for.  Instantiations
+// (see launch_eval_pruned): <256,2> (<= 128 registers) where shared memory admits two CTAs (2,048 points), <256,3>,
+// <256,4> (64 registers) below that, and <128,8> for meshes of <= 512 points: 16 blocks give a 256-thread CTA two
+// blocks per warp, and with three CTA barriers per pose ncu showed `barrier` as its top stall (2.7 warps per issue
+// cycle); half the CTA, twice the poses in flight.
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) adds_pruned_kernel(EvalArgs a, PrunedArgs pa, int nb_max, int nmax) {
+    constexpr int PR_WARPS = T / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int np_max = PR_BLOCK * nb_max;
     float* s_sorted = reinterpret_cast<float*>(smem_raw);
@@ -452,10 +454,9 @@ __global__ void __launch_bounds__(PR_T, MINB) adds_pruned_kernel(EvalArgs a, Pru
 static size_t g_pr_smem_raised[64];
 
 // The pruned kernel for one evaluation launch.  force = the explicit entry point (any mesh size that fits);
-// otherwise only when the table's switch is on and the table qualifies: below PR_MIN_POINTS the all-pairs kernel
-// is faster (32-point blocks are too coarse to skip much of a 500-point mesh, and its K = 4 / 8 register tiles
-// beat one pred point per lane), and a mesh that does not fit this kernel's shared memory takes the all-pairs
-// kernel as well.  *used tells the caller whether a launch happened.
+// otherwise only when the table's switch is on and the table qualifies: below PR_MIN_POINTS there is next to
+// nothing to skip, and a mesh that does not fit this kernel's shared memory takes the all-pairs kernel as well.
+// *used tells the caller whether a launch happened.
 int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaStream_t st, bool force, bool* used) {
     *used = false;
     PrunedTable* ptab = nullptr;
@@ -480,37 +481,38 @@ int launch_eval_pruned(const p6d_mesh_table* table, const EvalArgs& args, cudaSt
                           table->max_count, (limit - 1024) / 4 / 12 / 32 * 32);
                 return P6D_ETOOBIG;
             }
-            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            P6D_CUDA(cudaFuncSetAttribute(adds_pruned_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            for (const void* fn : {(const void*)adds_pruned_kernel<256, 2>, (const void*)adds_pruned_kernel<256, 3>,
+                                   (const void*)adds_pruned_kernel<256, 4>, (const void*)adds_pruned_kernel<128, 8>})
+                P6D_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             cur = smem;
         }
     }
     EvalArgs a = args;
     a.work_counter = table->d_counters + (__atomic_fetch_add(&table->counter_idx, 1u, __ATOMIC_RELAXED) % P6D_NUM_COUNTERS);
     P6D_CUDA(cudaMemsetAsync(a.work_counter, 0, sizeof(int), st));
-    // the instantiation whose register budget matches what shared memory lets be resident: 4 CTAs per SM
-    // (64 registers) for small meshes (+5-8 %), 3 (<= 80), or 2 (<= 128) at 2,048 points
-    int per_sm = 0, minb = 4;
-    P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<4>, PR_T, smem));
-    if (per_sm < 4) {
-        minb = 3;
-        P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<3>, PR_T, smem));
-        if (per_sm < 3) {
-            minb = 2;
-            P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, adds_pruned_kernel<2>, PR_T, smem));
+    // the instantiation whose register budget matches what shared memory lets be resident (see the kernel's comment)
+    struct Shape { const void* fn; int threads, minb; };
+    const Shape shapes[] = {{(const void*)adds_pruned_kernel<128, 8>, 128, 8}, {(const void*)adds_pruned_kernel<256, 4>, 256, 4},
+                            {(const void*)adds_pruned_kernel<256, 3>, 256, 3}, {(const void*)adds_pruned_kernel<256, 2>, 256, 2}};
+    const Shape* pick = &shapes[3];
+    int per_sm = 0;
+    for (const Shape& sh : shapes) {
+        if (sh.threads == 128 && nb > 16) continue;           // small CTAs for meshes of <= 512 points only
+        int occ = 0;
+        P6D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, sh.threads, smem));
+        if (occ >= sh.minb || &sh == &shapes[3]) {
+            pick = &sh;
+            per_sm = occ;
+            break;
         }
     }
     if (per_sm < 1) per_sm = 1;
     int64_t grid = static_cast<int64_t>(table->sm_count) * per_sm;
     if (grid > a.B) grid = a.B;
     PrunedArgs pa{ptab->d_sorted, ptab->d_slots};
-    if (minb == 4)
-        adds_pruned_kernel<4><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
-    else if (minb == 3)
-        adds_pruned_kernel<3><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
-    else
-        adds_pruned_kernel<2><<<static_cast<unsigned>(grid), PR_T, smem, st>>>(a, pa, nb, table->max_count);
+    int nb_arg = nb, nmax_arg = table->max_count;
+    void* kargs[] = {&a, &pa, &nb_arg, &nmax_arg};
+    P6D_CUDA(cudaLaunchKernel(pick->fn, dim3(static_cast<unsigned>(grid)), dim3(pick->threads), kargs, smem, st));
     P6D_CUDA(cudaGetLastError());
     *used = true;
     return P6D_OK;

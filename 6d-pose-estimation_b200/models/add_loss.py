@@ -79,7 +79,7 @@ class ADDLoss(nn.Module):
         # optional callable(indices, pred_r, pred_t, gt_r, gt_t, obj_ids) -> 0/1 per index, consulted by
         # eval_metrics for decisions flagged `borderline`; None (default): the kernel's decision stands
         self.borderline_resolver = None
-        # opt-in: exact block pruning in the ADD-S kernel (same bits; pays for meshes of >= 384 points, the
+        # opt-in: exact block pruning in the ADD-S kernel (same bits; pays for meshes of >= 128 points, the
         # all-pairs kernel is kept below that) -- not part of the reference surface, default off
         self.exact_pruning = False
         self._load_models(model_dir)

@@ -133,7 +133,7 @@ int p6d_add_eval(const p6d_mesh_table* table, const float* pq, const float* pt, 
  *   p6d_add_eval_pruned          always this kernel; adds must not be NULL; a table whose largest mesh exceeds
  *                                ~4,700 points (shared memory) or 65,534 points answers P6D_ETOOBIG
  *   p6d_mesh_table_set_pruning   per-table switch (default off): p6d_add_eval, p6d_add_eval_host and p6d_sweep_run
- *                                then take this kernel where it pays -- largest mesh of the table >= 384 points
+ *                                then take this kernel where it pays -- largest mesh of the table >= 128 points
  *                                and within the shared-memory limit -- and the all-pairs kernel otherwise
  *                                (the loss form p6d_add_forward always takes the all-pairs kernel). */
 int p6d_mesh_table_set_pruning(p6d_mesh_table* table, int enable);

@@ -13,6 +13,6 @@ ob = torch.full((Bn,), 9, dtype=torch.int64, device=dev)
 qa, ta = torch.nn.functional.normalize(rnd(Bn, 4), dim=1), rnd(Bn, 3)
 qb, tb = torch.nn.functional.normalize(qa + 0.05 * rnd(Bn, 4), dim=1), ta + 0.005 * rnd(Bn, 3)
 for _ in range(3):
-    t.evaluate(qb, tb, qa, ta, ob, want_adds=True)
+    t.evaluate(qb, tb, qa, ta, ob, want_adds=True, prune=bool(int(os.environ.get("PRUNE", "0"))))
 torch.cuda.synchronize()
 print("done")
