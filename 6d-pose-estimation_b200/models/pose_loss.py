@@ -157,8 +157,10 @@ class CapturedPoseLossStep:
     STATIC: write the network outputs into ``pred_rot`` / ``pred_trans`` (or ``z_pred`` /
     ``bbox_center`` / ``camera_matrix`` for the geometric form) and the targets into ``gt_rot`` /
     ``gt_trans`` (``copy_``, or let a captured network produce them in place), call ``replay()``, read
-    ``loss``, ``grad_rot`` and ``grad_trans`` (``grad_z`` for the geometric form).  ``__call__`` does
-    the copies for the caller (one fused ``_foreach_copy_``)."""
+    ``loss``, ``grad_rot`` and ``grad_trans`` (``grad_z`` for the geometric form).  ``__call__`` takes
+    the caller's own tensors: ready ones (float32, contiguous, on the device) are read in place by one
+    direct launch that writes the same static outputs; anything else is copied into the static
+    inputs (one fused ``_foreach_copy_``) and the graph replayed."""
 
     def __init__(self, criterion, pred_rot, pred_trans, gt_rot, gt_trans, geometric=None, warmup=3):
         dev = _core().require_cuda(pred_rot.device)
@@ -166,6 +168,7 @@ class CapturedPoseLossStep:
         self.pred_rot = static(pred_rot, True)
         self.gt_rot, self.gt_trans = static(gt_rot), static(gt_trans)
         self.geometric = geometric is not None
+        self._weights = (float(criterion.rot_weight), float(criterion.trans_weight), int(criterion._mode()))
         if self.geometric:            # pred_trans is z_pred; geometric = (bbox_center, camera_matrix)
             self.z_pred = static(pred_trans, True)
             self.bbox_center, self.camera_matrix = static(geometric[0]), static(geometric[1])
@@ -198,9 +201,39 @@ class CapturedPoseLossStep:
         self.graph.replay()
         return self.loss
 
+    def _launch_on(self, tensors):
+        """The captured step is ONE kernel (the backward's scale by 1 changes no bit), so for inputs that
+        are already what the kernel reads -- float32, contiguous, 16-byte aligned, on the device, of the
+        captured sizes -- it is launched straight on the caller's tensors, with the static ``loss`` /
+        ``grad_*`` / ``translation`` tensors as its outputs: no copies, no graph, ~one ctypes call.
+        Returns False when an input needs converting (the caller then copies and replays)."""
+        dev = self.pred_rot.device
+        for t, s in zip(tensors, self._ins):
+            if not (isinstance(t, torch.Tensor) and t.dtype is torch.float32 and t.device == dev and t.is_contiguous()
+                    and t.data_ptr() % 16 == 0 and t.numel() == s.numel()):
+                return False
+        core = _core()
+        B = self.pred_rot.numel() // 4
+        ws = _workspace(dev).data_ptr()
+        if self.geometric:
+            pq, z, uv, K, gq, gt = tensors
+            core.check(core.lib().p6d_pose_loss_pinhole_fwd_bwd(
+                pq.data_ptr(), z.data_ptr(), uv.data_ptr(), K.data_ptr(), 1 if self.camera_matrix.dim() == 3 else 0,
+                gq.data_ptr(), gt.data_ptr(), B, *self._weights, self.loss.data_ptr(), self.grad_rot.data_ptr(),
+                self.grad_z.data_ptr(), self.translation.data_ptr(), ws, dev.index, core.stream_ptr(dev)))
+        else:
+            pq, pt, gq, gt = tensors
+            core.check(core.lib().p6d_pose_loss_fwd_bwd(
+                pq.data_ptr(), pt.data_ptr(), gq.data_ptr(), gt.data_ptr(), B, *self._weights, self.loss.data_ptr(),
+                self.grad_rot.data_ptr(), self.grad_trans.data_ptr(), ws, dev.index, core.stream_ptr(dev)))
+        return True
+
     def __call__(self, *tensors):
         if len(tensors) != len(self._ins):
             raise ValueError(f"expected {len(self._ins)} tensors")
+        return self.loss if self._launch_on(tensors) else self.copy_and_replay(*tensors)
+
+    def copy_and_replay(self, *tensors):
         with torch.no_grad():
             torch._foreach_copy_(self._ins, [t.detach() for t in tensors])
         return self.replay()

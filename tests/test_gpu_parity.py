@@ -503,6 +503,13 @@ def test_captured_training_step_equals_the_eager_step(pkg, cuda_dev, W):
         got = step(rot, tr, Tn(c["gt_rot"]), Tn(c["gt_trans"]))
         assert got.item() == loss.item()
         assert torch.equal(step.grad_rot, rot.grad) and torch.equal(step.grad_trans, tr.grad)
+        # inputs the kernel cannot read in place (float64, a strided view) take the copy + replay path
+        step.grad_rot.zero_(); step.grad_trans.zero_()
+        wide = torch.stack([tr.detach(), tr.detach()], 1)[:, 0]
+        assert not wide.is_contiguous()
+        got = step(rot.detach().double(), wide, Tn(c["gt_rot"]), Tn(c["gt_trans"]))
+        assert got.item() == loss.item()
+        assert torch.equal(step.grad_rot, rot.grad) and torch.equal(step.grad_trans, tr.grad)
         rot2 = Tn(c["rot_raw"]).requires_grad_(True)
         z = Tn(c["z_pred"]).requires_grad_(True)
         l2, trans = crit.forward_geometric(rot2, z, Tn(c["bbox_center"]), Tn(c["K"]), Tn(c["gt_rot"]), Tn(c["gt_trans"]))
