@@ -403,8 +403,11 @@ def secondary_rooflines(pkg, dev, hbm_peak, fp32_peak):
     xyzb = torch.empty(big.shape[0], 3, device=dev)
     t = timed(lambda: core.check(L.p6d_depth_crop_backproject(dfr.data_ptr(), 480, 640, big.data_ptr(), big.shape[0], K1.data_ptr(),
                                                               224, 0, xyzb.data_ptr(), None, None, None, dev.index, st)))
-    hbm_row("depth_crop_backproject (N1), 2^20 boxes of one frame (frame stays in L2: 16 B box + 12 B out per row)",
-            big.shape[0], 28, t)
+    # ~330 warp instructions per box (the reference's float64 crop geometry, two float64 divisions per axis) on a
+    # frame that stays in L2: issue / latency bound (ncu: issue slots 46 %, DRAM 10 %), the GB/s is informational
+    res.append({"kernel": "depth_crop_backproject (N1), 2^20 boxes of one frame (frame stays in L2: 16 B box + 12 B out per row)",
+                "bound": "issue/latency", "rows": big.shape[0], "us": round(t * 1e6, 1), "boxes_per_s": big.shape[0] / t,
+                "hbm_gbs": big.shape[0] * 28 / t / 1e9})
     # N1, inference form: integer xyxy detector boxes, float32 resize, float64 centre / K_crop
     xyxy = bx.clone()
     xyxy[:, 2:] += xyxy[:, :2]
