@@ -39,6 +39,15 @@ def _ready(t, dev, tail):
     return _core().as_cuda_f32(t, dev, tail)
 
 
+def _row_major(shape):
+    """Contiguous strides of `shape`."""
+    strides, step = [], 1
+    for n in reversed(shape):
+        strides.append(step)
+        step *= max(int(n), 1)
+    return tuple(reversed(strides))
+
+
 def _empty_batch_nan(*tensors):
     """The reference on an empty batch: mean over zero rows -> NaN, attached to the inputs' graph."""
     total = None
@@ -82,13 +91,15 @@ class _FusedPoseLoss(torch.autograd.Function):
     def backward(ctx, grad_out):
         rs, ts, rd, td, need_q, need_t, B = ctx.meta
         # pick 0: d loss; pick 1: d rot_term (the kernel ran with rot_weight 1, trans_weight 0)
-        scaled = ctx.buf[:7 * B] * grad_out
+        # three torch ops instead of six: the whole buffer scaled at once (its tail -- padding and the loss
+        # terms -- is never looked at), each gradient one as_strided view of the product
+        scaled = ctx.buf * grad_out
         dq = dt = None
         if need_q:
-            dq = scaled[:4 * B].view(rs)
+            dq = scaled.as_strided(rs, _row_major(rs), 0)
             dq = dq if rd is torch.float32 else dq.to(rd)
         if need_t:
-            dt = scaled[4 * B:].view(ts)
+            dt = scaled.as_strided(ts, _row_major(ts), 4 * B)
             dt = dt if td is torch.float32 else dt.to(td)
         return dq, dt, None, None, None, None, None, None
 
@@ -136,13 +147,13 @@ class _FusedGeometricPoseLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss, _grad_trans):
         rs, zs, rd, zd, need_q, need_z, B = ctx.meta
-        scaled = ctx.buf[:5 * B] * grad_loss
+        scaled = ctx.buf * grad_loss
         dq = dz = None
         if need_q:
-            dq = scaled[:4 * B].view(rs)
+            dq = scaled.as_strided(rs, _row_major(rs), 0)
             dq = dq if rd is torch.float32 else dq.to(rd)
         if need_z:
-            dz = scaled[4 * B:].view(zs)
+            dz = scaled.as_strided(zs, _row_major(zs), 4 * B)
             dz = dz if zd is torch.float32 else dz.to(zd)
         return dq, dz, None, None, None, None, None, None, None
 
