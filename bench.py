@@ -161,7 +161,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons),
+                "sm_mhz_min": min(sm) if sm else None}
 
 
 # ------------------------------------------------------------------------- CPU arms
@@ -518,10 +519,14 @@ def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barr
     # a sweep of a second or two is ONE shot of ~180 launches per rank: a single host or box hiccup shows up whole
     # (r2as, 2 GPUs: 1.92 s once against 1.21 s on three repeats), so the short sweeps are timed twice, the
     # faster run is reported, both are listed and their integer hit tables must be identical
-    runs, first_hits = [], None
+    runs, first_hits, run_clocks = [], None, []
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     for _ in range(2 if n_points <= 1024 else 1):
         ev.acc.zero_()
+        sampler = ClockSampler(dev.index)        # every rank watches its own GPU: a slow run should name its cause
+        sampler.start()
         barrier()
+        sampler.mark_begin()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
@@ -530,10 +535,17 @@ def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barr
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        tm = torch.tensor([wall, e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
+        sampler.mark_end()
+        ck = sampler.stop()
+        # max over ranks of [wall, device time, -min SM clock, power, one flag per throttle reason]
+        tm = torch.tensor([wall, e0.elapsed_time(e1) * 1e-3, -(ck.get("sm_mhz_min") or 0.0), ck.get("power_w_max") or 0.0]
+                          + [float(n in ck["reasons"]) for n in names], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        runs.append(tuple(float(x) for x in tm.tolist()))
+        tm = tm.tolist()
+        runs.append((float(tm[0]), float(tm[1])))
+        run_clocks.append({"sm_mhz_min_over_ranks": -tm[2] or None, "power_w_max_over_ranks": tm[3] or None,
+                           "reasons_any_rank": [n for n, f in zip(names, tm[4:]) if f > 0]})
         if first_hits is None:
             first_hits = acc.hits.clone()
         elif not torch.equal(first_hits, acc.hits):
@@ -560,6 +572,7 @@ def sweep_record(pkg, dev, rank, world, n_points, n_per_block, check_total, barr
             "n_points": n_points, "hypotheses": total, "scaling": "strong", "n_gpus": world,
             "adds_kernel": "exact-pruned (opt-in)" if exact_pruning else "all-pairs",
             "seconds": wall_s, "device_seconds": dev_s, "seconds_of_every_run": [r[0] for r in runs],
+            "clocks_of_every_run": run_clocks,
             "poses_per_s": total / wall_s,
             "tflops": total * (8 * n_points * n_points + 46 * n_points) / wall_s / 1e12,
             "launches_per_rank": launches,
