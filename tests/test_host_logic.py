@@ -166,6 +166,34 @@ def test_no_cpu_fallback(pkg):
         pkg.depth_backproject(torch.ones(2, 224, 224), z(2), torch.eye(3))
 
 
+def test_backward_views_of_the_pose_loss_buffer(pkg):
+    """PoseLoss.backward takes each gradient as ONE as_strided view of the scaled buffer: the strides it
+    computes are torch's contiguous strides, and the views equal the slice + view they replaced."""
+    rm = pkg.models.pose_loss._row_major
+    for shape in [(32, 4), (32, 3), (32, 1), (32,), (5, 2, 4), (1, 4), (7, 1, 3)]:
+        assert rm(torch.Size(shape)) == torch.empty(shape).stride()
+    B = 6
+    buf = torch.arange((7 * B + 3) // 4 * 4 + 4, dtype=torch.float32)
+    scaled = buf * 3.0
+    rs, ts = torch.Size((B, 4)), torch.Size((3, 2, 3))
+    assert torch.equal(scaled.as_strided(rs, rm(rs), 0), (buf[:7 * B] * 3.0)[:4 * B].view(rs))
+    assert torch.equal(scaled.as_strided(ts, rm(ts), 4 * B), (buf[:7 * B] * 3.0)[4 * B:].view(ts))
+
+
+def test_current_stream_accessor_has_a_fallback(pkg, monkeypatch):
+    """stream_ptr uses torch's raw accessor when it exists and torch.cuda.current_stream otherwise."""
+    core = pkg.core
+    monkeypatch.setattr(core, "_raw_stream", lambda index: 1234 + index)
+    assert core.stream_ptr(torch.device("cuda", 3)) == 1237
+    calls = []
+
+    class _S:
+        cuda_stream = 77
+    monkeypatch.setattr(core, "_raw_stream", None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: calls.append(d) or _S())
+    assert core.stream_ptr(torch.device("cuda", 0)) == 77 and calls == [torch.device("cuda", 0)]
+
+
 def test_product_never_imports_the_oracle():
     """Nothing under the package imports, loads or links oracle/ (comments may cite it)."""
     root = os.path.join(REPO, "6d-pose-estimation_b200")
