@@ -19,8 +19,6 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
 pts, dia = pkg.workloads.sweep_meshes(n_points)
 pkg.evaluate_sweep(pts, dia, dev, 4096, rank=rank, world=world)          # warm-up (kernels, NCCL)
@@ -28,7 +26,7 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-acc, launches = pkg.evaluate_sweep(pts, dia, dev, n_per_block, rank=rank, world=world)
+acc, launches, _ = pkg.evaluate_sweep(pts, dia, dev, n_per_block, rank=rank, world=world)
 torch.cuda.synchronize()
 dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
 if world > 1:
@@ -41,6 +39,6 @@ if rank == 0:
                       "launches_per_rank": launches, "valid_total": int(acc.valid.sum().item()),
                       "add_01d_acc_by_variant": {v: round(tab[v]["all"]["add_01d_acc"], 4) for v in pkg.sweep.VARIANTS},
                       "hits_total": int(acc.hits.sum().item()),
-                      "note": "includes on-device generation of the synthetic hypotheses (torch RNG) and the translation kernels"}))
+                      "note": "includes on-device generation of the synthetic hypotheses (p6d_synth_poses) and the translation kernels"}))
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
